@@ -1,0 +1,211 @@
+"""ctypes binding of libaon_b200.so (C ABI declared in include/aon.h).
+
+The product path FAILS LOUDLY when the library is missing or a call fails -- there is no CPU /
+eager fallback anywhere in this package.  torch is used only as the owner of device memory and
+streams: every wrapper takes CUDA fp32 contiguous tensors and passes raw pointers + the current
+stream to the C entry points.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaon_b200.so")
+
+KIND_VANILLA, KIND_AUTODECODER = 0, 1
+PREC_FP32, PREC_TC_F16X3, PREC_TC_F16, PREC_TC_BF16 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "f16x3": PREC_TC_F16X3, "f16": PREC_TC_F16, "bf16": PREC_TC_BF16}
+
+# every symbol include/aon.h declares: name -> (restype, argtypes)
+_vp, _fp, _i, _l, _f, _sz = C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_size_t
+SYMBOLS = {
+    "aon_version": (_i, []),
+    "aon_last_error": (C.c_char_p, []),
+    "aon_num_layers": (_i, [_i]),
+    "aon_layer_shape": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "aon_packed_bytes": (_sz, [_i, _i]),
+    "aon_pack_weights": (_i, [_i, _i, C.POINTER(_vp), C.POINTER(_vp), _vp, _sz, _vp]),
+    "aon_folded_floats": (_sz, [_i]),
+    "aon_fold_latents": (_i, [_i, _i, _vp, _fp, _fp, _fp, _fp, _vp]),
+    "aon_raygen": (_i, [_i, _i, _f, C.POINTER(_f), _fp, _fp, _vp]),
+    "aon_sample_along_rays": (_i, [_f, _f, _i, _fp, _i, _fp, _vp]),
+    "aon_render_level": (_i, [_i, _i, _vp, _fp, _fp, _fp, _fp, _fp, _l, _i, _i, _i, _fp, _fp, _fp, _fp, _vp]),
+    "aon_sample_pdf": (_i, [_fp, _l, _fp, _fp, _l, _i, _i, _i, _fp, _vp]),
+    "aon_render_image_host": (_i, [_i, _i, _vp, _vp, _fp, _fp, _fp, _fp, _fp, _i, _f, _f, _i, _fp, _fp, _vp]),
+    "aon_launch_count": (_l, [_i]),
+}
+
+
+class AonError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the library (once).  Raises AonError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AonError("libaon_b200.so is not built (%s missing): run `python -c 'import __graft_entry__ as g; "
+                       "g.build()'` or `python articulated-object-nerf_b200/build.py`" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise AonError("%s failed (%d): %s" % (what, rc, load().aon_last_error().decode()))
+
+
+def _ptr(t: Optional[torch.Tensor], what: str = "tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise AonError("%s must be a contiguous CUDA float32 tensor (got %s %s contiguous=%s)"
+                       % (what, t.device, t.dtype, t.is_contiguous()))
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(load().aon_launch_count(1 if reset else 0))
+
+
+def layer_shapes(kind: int) -> List[tuple]:
+    lib = load()
+    out = []
+    for i in range(lib.aon_num_layers(kind)):
+        o, k = C.c_int(), C.c_int()
+        _check(lib.aon_layer_shape(kind, i, C.byref(o), C.byref(k)), "aon_layer_shape")
+        out.append((o.value, k.value))
+    return out
+
+
+def pack_weights(kind: int, precision: int, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[out,in] fp32 nn.Linear weights (state_dict order) -> kernel layout.  Returns a uint8 CUDA tensor."""
+    lib = load()
+    n = lib.aon_num_layers(kind)
+    if len(weights) != n or len(biases) != n:
+        raise AonError("expected %d layers, got %d/%d" % (n, len(weights), len(biases)))
+    shapes = layer_shapes(kind)
+    keep = []
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        if tuple(w.shape) != shapes[i] or tuple(b.shape) != (shapes[i][0],):
+            raise AonError("layer %d: expected weight %s, got %s / bias %s" % (i, shapes[i], tuple(w.shape), tuple(b.shape)))
+        keep.append((w.detach().contiguous().float(), b.detach().contiguous().float()))
+    nbytes = lib.aon_packed_bytes(kind, precision)
+    if nbytes == 0:
+        raise AonError("aon_packed_bytes: unsupported kind/precision %d/%d" % (kind, precision))
+    dev = keep[0][0].device
+    if out is None:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    wp = (C.c_void_p * n)(*[_ptr(w, "weight") for w, _ in keep])
+    bp = (C.c_void_p * n)(*[_ptr(b, "bias") for _, b in keep])
+    with torch.cuda.device(dev):
+        _check(lib.aon_pack_weights(kind, precision, wp, bp, out.data_ptr(), out.numel(), _stream()), "aon_pack_weights")
+    return out
+
+
+def fold_latents(kind: int, precision: int, packed: torch.Tensor, shape: torch.Tensor, appearance: torch.Tensor,
+                 articulation: torch.Tensor) -> torch.Tensor:
+    lib = load()
+    folded = torch.empty(lib.aon_folded_floats(kind), dtype=torch.float32, device=packed.device)
+    with torch.cuda.device(packed.device):
+        _check(lib.aon_fold_latents(kind, precision, packed.data_ptr(), _ptr(shape.reshape(-1), "shape"),
+                                    _ptr(appearance.reshape(-1), "appearance"),
+                                    _ptr(articulation.reshape(-1), "articulation"), _ptr(folded), _stream()),
+               "aon_fold_latents")
+    return folded
+
+
+def raygen(H: int, W: int, focal: float, c2w, device) -> tuple:
+    """A1+A2: (rays_o [HW,3], rays_d [HW,3]); rays_d is unit-norm and doubles as viewdirs."""
+    lib = load()
+    c = torch.as_tensor(c2w, dtype=torch.float32).reshape(-1)[:12].cpu().contiguous()
+    arr = (C.c_float * 12)(*c.tolist())
+    o = torch.empty(H * W, 3, dtype=torch.float32, device=device)
+    d = torch.empty(H * W, 3, dtype=torch.float32, device=device)
+    with torch.cuda.device(o.device):
+        _check(lib.aon_raygen(H, W, float(focal), arr, _ptr(o), _ptr(d), _stream()), "aon_raygen")
+    return o, d
+
+
+def sample_along_rays(near: float, far: float, n_points: int, R: int, device, t_rand: Optional[torch.Tensor] = None):
+    """A3: deterministic -> shared table [n_points]; with t_rand [R,n_points] -> [R,n_points]."""
+    lib = load()
+    shape = (n_points,) if t_rand is None else (R, n_points)
+    t = torch.empty(shape, dtype=torch.float32, device=device)
+    with torch.cuda.device(t.device):
+        _check(lib.aon_sample_along_rays(float(near), float(far), n_points, _ptr(t_rand, "t_rand"), R, _ptr(t), _stream()),
+               "aon_sample_along_rays")
+    return t
+
+
+def render_level(kind: int, precision: int, packed: torch.Tensor, folded: Optional[torch.Tensor], rays_o, rays_d,
+                 viewdirs, t_vals: torch.Tensor, white_bkgd: bool, want_weights: bool = True):
+    """One level.  t_vals [S] (shared) or [R,S].  Returns (comp_rgb [R,3], acc [R], depth [R], weights [R,S]|None)."""
+    lib = load()
+    R = rays_o.shape[0]
+    S = t_vals.shape[-1]
+    stride = 0 if t_vals.dim() == 1 else S
+    dev = rays_o.device
+    rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
+    acc = torch.empty(R, dtype=torch.float32, device=dev)
+    depth = torch.empty(R, dtype=torch.float32, device=dev)
+    w = torch.empty(R, S, dtype=torch.float32, device=dev) if want_weights else None
+    with torch.cuda.device(dev):
+        _check(lib.aon_render_level(kind, precision, packed.data_ptr(), _ptr(folded, "folded"), _ptr(rays_o, "rays_o"),
+                                    _ptr(rays_d, "rays_d"), _ptr(viewdirs, "viewdirs"), _ptr(t_vals, "t_vals"), stride,
+                                    R, S, int(bool(white_bkgd)), _ptr(rgb), _ptr(acc), _ptr(depth), _ptr(w), _stream()),
+               "aon_render_level")
+    return rgb, acc, depth, w
+
+
+def sample_pdf(t_coarse: torch.Tensor, weights: torch.Tensor, n_fine: int, u: Optional[torch.Tensor] = None):
+    """A7: t_coarse [n_coarse] or [R,n_coarse]; weights [R,n_coarse]; u None | [n_fine] | [R,n_fine]."""
+    lib = load()
+    R, nc = weights.shape
+    t_stride = 0 if t_coarse.dim() == 1 else nc
+    u_stride = 0 if (u is None or u.dim() == 1) else n_fine
+    out = torch.empty(R, nc + n_fine, dtype=torch.float32, device=weights.device)
+    with torch.cuda.device(weights.device):
+        _check(lib.aon_sample_pdf(_ptr(t_coarse, "t_coarse"), t_stride, _ptr(weights, "weights"), _ptr(u, "u"), u_stride,
+                                  R, nc, n_fine, _ptr(out), _stream()), "aon_sample_pdf")
+    return out
+
+
+def render_image_host(kind: int, precision: int, packed_coarse, packed_fine, folded_coarse, folded_fine,
+                      rays_o: torch.Tensor, rays_d: torch.Tensor, viewdirs: torch.Tensor, near: float, far: float,
+                      white_bkgd: bool, out: Optional[torch.Tensor] = None, coarse_out: Optional[torch.Tensor] = None):
+    """A8/A11 from HOST (ideally pinned) fp32 tensors; returns host [R,5] = rgb, acc, depth (fine level)."""
+    lib = load()
+    for t in (rays_o, rays_d, viewdirs):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise AonError("render_image_host takes contiguous CPU float32 tensors")
+    R = rays_o.shape[0]
+    if out is None:
+        out = torch.empty(R, 5, dtype=torch.float32).pin_memory()
+    dev = packed_coarse.device
+    with torch.cuda.device(dev):
+        _check(lib.aon_render_image_host(kind, precision, packed_coarse.data_ptr(), packed_fine.data_ptr(),
+                                         _ptr(folded_coarse, "folded"), _ptr(folded_fine, "folded"),
+                                         rays_o.data_ptr(), rays_d.data_ptr(), viewdirs.data_ptr(), R, float(near),
+                                         float(far), int(bool(white_bkgd)), out.data_ptr(),
+                                         None if coarse_out is None else coarse_out.data_ptr(), _stream()),
+               "aon_render_image_host")
+    return out

@@ -1,0 +1,140 @@
+/* aon.h -- C ABI of libaon_b200.so: the B200-native (sm_100a) volume-rendering hot path of
+ * zubair-irshad/articulated-object-nerf.
+ *
+ * The reference has NO native / FFI layer (it is 100 % Python on stock ATen ops);
+ * its de-facto boundary is the Python call NeRF.forward(rays, randomized, white_bkgd, near, far)
+ * (models/vanilla_nerf/model.py:147-199) and NeRF_AE_Art.forward(..., latents)
+ * (models/vanilla_nerf/model_autodecoder.py:278-337).  Each entry point below replaces the group of
+ * reference functions cited next to it; INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add to route those calls here.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative AON_E_* code; it never throws, exits or
+ *     prints.  aon_last_error() returns a thread-local message for the last failure.
+ *   - all tensor pointers are DEVICE pointers to contiguous row-major fp32 unless the name ends in
+ *     _host; the caller allocates everything (no hidden allocation, no global mutable state);
+ *     the one exception is aon_render_image_host(), which owns a scratch arena it creates lazily.
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream); no entry point synchronises unless it says so.
+ *   - the device is the calling thread's current CUDA device.
+ */
+#ifndef AON_H_
+#define AON_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AON_ABI_VERSION 1
+
+/* error codes */
+#define AON_OK 0
+#define AON_E_ARG (-1)      /* bad argument (null pointer, bad size, misaligned pointer)        */
+#define AON_E_CUDA (-2)     /* a CUDA runtime call failed; see aon_last_error()                 */
+#define AON_E_UNSUPPORTED (-3) /* valid request this build/device cannot serve (e.g. not sm_100) */
+#define AON_E_SIZE (-4)     /* caller buffer too small                                          */
+
+/* model kind: which of the reference's two hard-coded MLPs */
+#define AON_KIND_VANILLA 0     /* models/vanilla_nerf/model.py:39-120            (12 linears)  */
+#define AON_KIND_AUTODECODER 1 /* models/vanilla_nerf/model_autodecoder.py:60-239 (20 linears)  */
+
+/* arithmetic mode of the MLP contraction */
+#define AON_PREC_FP32 0    /* fp32 FFMA on CUDA cores (exact-order-free fp32; the parity anchor)   */
+#define AON_PREC_TC_F16X3 1 /* tcgen05 kind::f16, operands split hi+lo fp16 (3 MMAs, ~22-bit)      */
+#define AON_PREC_TC_F16 2  /* tcgen05 kind::f16, single fp16 operands (fast mode)                  */
+#define AON_PREC_TC_BF16 3 /* tcgen05 kind::f16, single bf16 operands (fast mode, wide range)      */
+
+typedef void* aon_stream_t; /* cudaStream_t */
+
+int aon_version(void);
+const char* aon_last_error(void);
+
+/* Number of nn.Linear layers of a kind, in the reference's state_dict order
+ * (vanilla: pts_linears.0-7, views_linear.0, bottleneck_layer, density_layer, rgb_layer;
+ *  auto-decoder: deformations_linear.0-3, deformation_layer, pts_linears.0-7, views_linear.0-3,
+ *  bottleneck_layer, density_layer, rgb_layer). */
+int aon_num_layers(int kind);
+/* out/in features of layer `i` of `kind` (the reference [out,in] weight shape). */
+int aon_layer_shape(int kind, int i, int* out_features, int* in_features);
+
+/* ---- weight packing -------------------------------------------------------------------------
+ * Replaces nothing in the reference (it keeps nn.Linear [out,in] fp32); converts ONE MLP
+ * (coarse_mlp or fine_mlp) from that layout into the kernel layout of `precision`.
+ * w[i]/b[i]: device pointers to layer i's weight [out,in] and bias [out], i < aon_num_layers(kind).
+ * `w`/`b` themselves are HOST arrays of device pointers. */
+size_t aon_packed_bytes(int kind, int precision);
+int aon_pack_weights(int kind, int precision, const float* const* w, const float* const* b,
+                     void* packed, size_t packed_bytes, aon_stream_t stream);
+
+/* ---- latent folding (auto-decoder only) --------------------------------------------------------
+ * Replaces the einops.repeat broadcast + concat of the latent codes to every sample
+ * (model_autodecoder.py:186-198, :226-228): the latent columns of deformations_linear.0,
+ * pts_linears.0, pts_linears.5 and views_linear.0 are contracted with the codes ONCE per call into
+ * per-call bias vectors.  shape/appearance [128], articulation [32] (device).  `folded` receives
+ * aon_folded_floats(kind) floats and is passed to aon_render_level(). */
+size_t aon_folded_floats(int kind);
+int aon_fold_latents(int kind, int precision, const void* packed, const float* shape,
+                     const float* appearance, const float* articulation, float* folded,
+                     aon_stream_t stream);
+
+/* ---- A1+A2  ray generation ---------------------------------------------------------------------
+ * Replaces get_ray_directions + get_rays(output_view_dirs=True) (datasets/ray_utils.py:71-90,
+ * :118-159).  c2w_host: 12 floats, row-major [3,4], read on the host at call time.
+ * rays_o / rays_d: [H*W,3]; rays_d is unit-norm and doubles as viewdirs (the reference returns the
+ * same values for both, ray_utils.py:146-147). */
+int aon_raygen(int H, int W, float focal, const float* c2w_host, float* rays_o, float* rays_d,
+               aon_stream_t stream);
+
+/* ---- A3  coarse sampling -----------------------------------------------------------------------
+ * Replaces sample_along_rays (helper.py:106-133), lindisp=False.  n_points = num_samples+1 (65).
+ * t_rand == NULL: deterministic -> writes the shared table t_vals[n_points] (the reference
+ * broadcasts it);  else t_rand [R,n_points] uniform -> stratified jitter, t_vals [R,n_points]. */
+int aon_sample_along_rays(float near, float far, int n_points, const float* t_rand, int R,
+                          float* t_vals, aon_stream_t stream);
+
+/* ---- A4+A5/A9+A6  one level: encode, MLP, activations, alpha compositing ---------------------------
+ * Replaces, per level, cast_rays + pos_enc + NeRFMLP.forward + activations + volumetric_rendering
+ * (helper.py:25-26,136-140,157-195; model.py:95-120,174-195; model_autodecoder.py:171-239,306-331).
+ * t_vals: [R,S] (t_stride = S) or a shared table [S] (t_stride = 0).
+ * folded: from aon_fold_latents() (auto-decoder) or NULL (vanilla).
+ * Outputs: comp_rgb [R,3], acc [R], depth [R]; weights [R,S] may be NULL. */
+int aon_render_level(int kind, int precision, const void* packed, const float* folded,
+                     const float* rays_o, const float* rays_d, const float* viewdirs,
+                     const float* t_vals, long t_stride, int R, int S, int white_bkgd,
+                     float* comp_rgb, float* acc, float* depth, float* weights,
+                     aon_stream_t stream);
+
+/* ---- A7  hierarchical sampling ------------------------------------------------------------------
+ * Replaces the t_mids / weights[...,1:-1] slicing (model.py:162-166) + sample_pdf
+ * (helper.py:203-252): t_coarse [R,n_coarse] (stride 0 = shared table), weights [R,n_coarse]
+ * (the full compositing weights; the kernel drops the first and last itself),
+ * u [R,n_fine] or [n_fine] (u_stride 0) or NULL = the reference's deterministic linspace;
+ * t_fine [R, n_coarse+n_fine] sorted.  n_coarse <= 65, n_fine <= 128. */
+int aon_sample_pdf(const float* t_coarse, long t_stride, const float* weights, const float* u,
+                   long u_stride, int R, int n_coarse, int n_fine, float* t_fine,
+                   aon_stream_t stream);
+
+/* ---- A8/A11  whole-image render from HOST buffers ----------------------------------------------
+ * Replaces render_rays / render_rays_test's chunk loop over NeRF.forward (model.py:295-348;
+ * model_autodecoder.py:479-541) for deterministic eval: host rays in, host pixels out.  Does
+ * H2D copies, coarse level, sample_pdf, fine level, D2H copies on `stream` and SYNCHRONISES it.
+ * rays_*_host [R,3]; out_host [R,5] = (r,g,b,acc,depth) of the FINE level;
+ * coarse_out_host [R,5] may be NULL.  packed_coarse/fine + folded_* are device pointers. */
+int aon_render_image_host(int kind, int precision, const void* packed_coarse,
+                          const void* packed_fine, const float* folded_coarse,
+                          const float* folded_fine, const float* rays_o_host,
+                          const float* rays_d_host, const float* viewdirs_host, int R, float near,
+                          float far, int white_bkgd, float* out_host, float* coarse_out_host,
+                          aon_stream_t stream);
+
+/* Number of kernels launched by this library on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+long aon_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AON_H_ */

@@ -1,0 +1,61 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/aon.h declares.
+No compute calls (no GPU here); argument validation paths that return before touching CUDA are exercised."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "aon.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(aon_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(built_lib):
+    lib = built_lib.load()
+    names = declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), "libaon_b200.so does not export %s" % n
+    assert set(names) == set(built_lib.SYMBOLS), "lib.py binding table out of sync with include/aon.h"
+
+
+def test_introspection(built_lib):
+    lib = built_lib.load()
+    assert lib.aon_version() == 1
+    assert lib.aon_num_layers(0) == 12 and lib.aon_num_layers(1) == 20 and lib.aon_num_layers(7) < 0
+    from oracle import ref_cpu as O
+    assert built_lib.layer_shapes(0) == [(o, i) for _, o, i in O.VANILLA_LAYERS]
+    assert built_lib.layer_shapes(1) == [(o, i) for _, o, i in O.AUTODECODER_LAYERS]
+    assert lib.aon_packed_bytes(0, 0) > 4 * 593408 and lib.aon_packed_bytes(1, 0) > 4 * 600000
+    assert lib.aon_packed_bytes(0, 99) == 0
+    assert lib.aon_folded_floats(0) == 0 and lib.aon_folded_floats(1) == 768 + 288
+
+
+def test_argument_errors_return_codes(built_lib):
+    lib = built_lib.load()
+    rc = lib.aon_render_level(0, 0, None, None, None, None, None, None, 0, 1, 65, 1, None, None, None, None, None)
+    assert rc == -1 and b"null" in lib.aon_last_error()
+    rc = lib.aon_sample_pdf(None, 0, None, None, 0, 1, 65, 128, None, None)
+    assert rc == -1
+    rc = lib.aon_raygen(0, 0, ctypes.c_float(1.0), None, None, None, None)
+    assert rc == -1
+
+
+def test_sass_is_sm100a(built_lib):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", built_lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "articulated-object-nerf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
