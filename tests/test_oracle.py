@@ -117,3 +117,14 @@ def test_layer_tables_match_param_counts():
     # 595 844 / 798 215 params per MLP
     assert sum(o * i + o for _, o, i in O.VANILLA_LAYERS) == 595844
     assert sum(o * i + o for _, o, i in O.AUTODECODER_LAYERS) == 798215
+
+
+def test_product_synth_generators_match_oracle_copies(built_lib):
+    """bench.py / smoke() build their scenes with aon_b200.synth; the parity tests with the oracle's own
+    generators -- both must describe the same synthetic scene."""
+    from aon_b200 import synth
+    for kind in ("vanilla", "autodecoder"):
+        a, b = synth.make_state_dict(kind, 0, True), O.make_state_dict(kind, 0, True)
+        assert list(a) == list(b)
+        assert all(torch.equal(a[k], b[k]) for k in a)
+    assert torch.equal(synth.sapien_camera(3), O.sapien_camera(3))
