@@ -209,3 +209,23 @@ def render_image_host(kind: int, precision: int, packed_coarse, packed_fine, fol
                                          None if coarse_out is None else coarse_out.data_ptr(), _stream()),
                "aon_render_image_host")
     return out
+
+
+# ---- debug hooks (exported by the library but deliberately not part of include/aon.h) ------------------
+def debug_program_info(kind: int, precision: int) -> dict:
+    lib = load()
+    lib.aon_debug_program_info.restype = C.c_int
+    lib.aon_debug_program_info.argtypes = [_i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    lib.aon_debug_program_info(kind, precision, C.byref(a), C.byref(b), C.byref(c))
+    return {"n_units": a.value, "n_stages": b.value, "smem_bytes": c.value}
+
+
+def debug_set_buffers(dbg: Optional[torch.Tensor], err: Optional[torch.Tensor]) -> None:
+    """dbg: CUDA float32 [n_units,128,128] receiving the pre-activation outputs of every unit for ray
+    tile 0 / sample 0 of subsequent tensor-core render_level calls; err: CUDA int32 [1] receiving a code
+    if a pipeline barrier times out.  Pass None, None to switch both off."""
+    lib = load()
+    lib.aon_debug_set_buffers.restype = None
+    lib.aon_debug_set_buffers.argtypes = [_vp, _vp]
+    lib.aon_debug_set_buffers(None if dbg is None else dbg.data_ptr(), None if err is None else err.data_ptr())
