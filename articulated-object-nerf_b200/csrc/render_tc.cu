@@ -32,29 +32,38 @@ namespace aon {
 void layout_tail(int kind, PackedLayout& L, int64_t off);  // aon_api.cu
 
 // ---- program (unit schedule), built on the host, passed to the kernels by value ------------------
-constexpr int MAX_UNITS = 28;
+constexpr int MAX_UNITS = 18;
+constexpr int MAX_CHUNKS = 10;
 constexpr int CH_E0 = 8, CH_V = 10, CH_P = 11, NUM_CHUNK_IDS = 12;
-constexpr int STAGE_BYTES = 8192;
 enum Epi : int { EPI_STORE = 0, EPI_STORE_SIGMA = 1, EPI_RGB = 2, EPI_DEFORM = 3 };
 
+// shared-memory offsets of the operand regions (bytes from the 1024-aligned base); host and device
+constexpr int OFF_A = 0;
+__host__ __device__ constexpr int off_E(bool x3) { return x3 ? 131072 : 65536; }
+__host__ __device__ constexpr int off_V(bool x3) { return off_E(x3) + (x3 ? 32768 : 16384); }
+__host__ __device__ constexpr int off_P(bool x3) { return off_V(x3) + (x3 ? 16384 : 8192); }
+constexpr int LO_A = 65536, LO_E = 16384, LO_V = 8192, LO_P = 4096;  // hi -> lo part (x3 only)
+
+// chunk word: [0,16) operand offset >> 4 | [16,20) chunk id | 20 fresh (first use of a generation: wait)
+//             | 21 writes-per-sample odd | 22 generation parity within a sample | [23,25) K steps of 16
+//             | [25,30) (lo part offset) >> 12
 struct Unit {
-  uint8_t gemm, half, n_chunks, epi;
-  uint8_t relu, in_buf, out_buf, wait_next;
-  uint8_t chunk[12];
-  uint8_t gen[12];
+  uint8_t gemm, n_chunks, epi, relu;
+  uint8_t n128;        // N / 128 (1 or 2)
+  uint8_t last_e_use;  // the encoding operand may be overwritten once this unit's MMAs have completed
   uint16_t bias_off;
-  uint16_t stage0;  // first weight stage of this unit within a sample
+  uint32_t ch[MAX_CHUNKS];
 };
 
 struct Program {
-  int n_units, n_stages, n_bias, x3;
-  int n_gemm;
-  int wps[NUM_CHUNK_IDS];  // writes per sample of each chunk id
+  int n_units, n_gemm, x3;
+  long stream_bytes;           // weight stream bytes per sample
   uint16_t layer_n[MAX_GEMM];  // out features of each GEMM layer (bias vector lengths)
   Unit u[MAX_UNITS];
 };
 
-static int stages_of_chunk(int id, int x3) { return x3 ? (id == CH_P ? 1 : 2) : 1; }
+__host__ __device__ inline int unit_stage_bytes(const Unit& u, int x3) { return u.n128 * 128 * (x3 ? 32 : 64); }
+__host__ __device__ inline int chunk_stages(uint32_t w, int x3) { return x3 ? 2 * (int)((w >> 23) & 3) : 1; }
 
 static Program build_program(int kind, int precision) {
   Program P;
@@ -63,13 +72,16 @@ static Program build_program(int kind, int precision) {
   P.x3 = x3;
   const GemmLayer* g = gemm_layers(kind);
   const int ng = num_gemm(kind);
-  int count[NUM_CHUNK_IDS] = {0};
+  int count[NUM_CHUNK_IDS] = {0}, seen_gen[NUM_CHUNK_IDS];
+  for (int i = 0; i < NUM_CHUNK_IDS; ++i) seen_gen[i] = -1;
   if (kind == AON_KIND_VANILLA) count[CH_E0] = count[CH_E0 + 1] = 1;
   else count[CH_P] = 1;
   count[CH_V] = 1;
-  int bias_pref = 0, stage = 0, nu = 0;
+  struct Use { int ui, c, id, gen; };
+  Use uses[MAX_UNITS * MAX_CHUNKS];
+  int n_uses = 0, bias_pref = 0, last_e = -1;
   for (int gi = 0; gi < ng; ++gi) {
-    const int halves = g[gi].N / 128;
+    Unit& u = P.u[gi];
     int epi = EPI_STORE;
     if (kind == AON_KIND_VANILLA) {
       if (gi == 7) epi = EPI_STORE_SIGMA;
@@ -79,40 +91,45 @@ static Program build_program(int kind, int precision) {
       if (gi == 11) epi = EPI_STORE_SIGMA;
       if (gi == 16) epi = EPI_RGB;
     }
-    for (int h = 0; h < halves; ++h) {
-      Unit& u = P.u[nu++];
-      u.gemm = gi; u.half = h; u.epi = epi; u.relu = g[gi].relu;
-      u.out_buf = x3 ? 0 : (gi & 1);
-      u.in_buf = x3 ? 0 : ((gi + 1) & 1);
-      u.wait_next = (x3 && halves == 2 && h == 0 && epi <= EPI_STORE_SIGMA) ? 1 : 0;
-      u.bias_off = (uint16_t)(bias_pref + h * 128);
-      u.stage0 = (uint16_t)stage;
-      int nc = 0;
-      for (int j = 0; j < g[gi].K1 / 32; ++j) u.chunk[nc++] = j;
-      if (g[gi].aux == AUX_E) { u.chunk[nc++] = CH_E0; u.chunk[nc++] = CH_E0 + 1; }
-      if (g[gi].aux == AUX_V) u.chunk[nc++] = CH_V;
-      if (g[gi].aux == AUX_P) u.chunk[nc++] = CH_P;
-      u.n_chunks = nc;
-      for (int c = 0; c < nc; ++c) {
-        u.gen[c] = (uint8_t)(count[u.chunk[c]] - 1);
-        stage += stages_of_chunk(u.chunk[c], x3);
-      }
-    }
-    // after both halves of the layer: its outputs become new generations of the A chunks
+    u.gemm = gi; u.epi = epi; u.relu = g[gi].relu; u.n128 = g[gi].N / 128;
+    u.bias_off = (uint16_t)bias_pref;
+    int ids[MAX_CHUNKS], nc = 0;
+    for (int j = 0; j < g[gi].K1 / 32; ++j) ids[nc++] = j;
+    if (g[gi].aux == AUX_E) { ids[nc++] = CH_E0; ids[nc++] = CH_E0 + 1; last_e = gi; }
+    if (g[gi].aux == AUX_V) ids[nc++] = CH_V;
+    if (g[gi].aux == AUX_P) ids[nc++] = CH_P;
+    u.n_chunks = nc;
+    for (int c = 0; c < nc; ++c) uses[n_uses++] = {gi, c, ids[c], count[ids[c]] - 1};
     if (epi <= EPI_STORE_SIGMA)
-      for (int j = 0; j < halves * 4; ++j) count[j]++;
+      for (int j = 0; j < u.n128 * 4; ++j) count[j]++;
     if (epi == EPI_DEFORM) { count[CH_E0]++; count[CH_E0 + 1]++; }
     bias_pref += g[gi].N;
   }
-  // generations consumed by a unit's first half must not see the layer's own writes: the loop above
-  // bumps the counts only after both halves, which is exactly that.
-  P.n_units = nu;
+  count[CH_V] = 0;  // written once per CTA: its generation never advances
+  long bytes = 0;
+  for (int i = 0; i < n_uses; ++i) {
+    const Use& x = uses[i];
+    int off, lo;
+    if (x.id < 8) { off = OFF_A + x.id * 8192; lo = LO_A; }
+    else if (x.id < CH_V) { off = off_E(x3) + (x.id - CH_E0) * 8192; lo = LO_E; }
+    else if (x.id == CH_V) { off = off_V(x3); lo = LO_V; }
+    else { off = off_P(x3); lo = LO_P; }
+    const int ksteps = (x3 && x.id == CH_P) ? 1 : 2;
+    const int fresh = x.gen != seen_gen[x.id] || x.id == CH_V;
+    seen_gen[x.id] = x.gen;
+    uint32_t w = (uint32_t)(off >> 4) | ((uint32_t)x.id << 16) | ((uint32_t)fresh << 20) |
+                 ((uint32_t)(count[x.id] & 1) << 21) | ((uint32_t)(x.gen & 1) << 22) | ((uint32_t)ksteps << 23) |
+                 ((uint32_t)(lo >> 12) << 25);
+    P.u[x.ui].ch[x.c] = w;
+  }
+  for (int gi = 0; gi < ng; ++gi) {
+    P.layer_n[gi] = (uint16_t)g[gi].N;
+    for (int c = 0; c < P.u[gi].n_chunks; ++c) bytes += (long)chunk_stages(P.u[gi].ch[c], x3) * unit_stage_bytes(P.u[gi], x3);
+  }
+  if (last_e >= 0) P.u[last_e].last_e_use = 1;
+  P.n_units = ng;
   P.n_gemm = ng;
-  for (int gi = 0; gi < ng; ++gi) P.layer_n[gi] = (uint16_t)g[gi].N;
-  P.n_stages = stage;
-  P.n_bias = bias_pref;
-  for (int i = 0; i < NUM_CHUNK_IDS; ++i) P.wps[i] = count[i];
-  P.wps[CH_V] = 0;  // written once per CTA
+  P.stream_bytes = bytes;
   return P;
 }
 
@@ -120,50 +137,46 @@ PackedLayout layout_tc(int kind, int precision) {
   PackedLayout L;
   memset(&L, 0, sizeof(L));
   const Program P = build_program(kind, precision);
-  for (int i = 0; i < num_gemm(kind); ++i) L.w[i] = 0;  // one contiguous stream, see Program::stage0
-  layout_tail(kind, L, (int64_t)P.n_stages * STAGE_BYTES);
+  for (int i = 0; i < num_gemm(kind); ++i) L.w[i] = 0;  // one contiguous stream in unit order
+  layout_tail(kind, L, (P.stream_bytes + 255) / 256 * 256);
   return L;
 }
 
 // ---- weight stream packing ----------------------------------------------------------------------------
-// Stage layout (8 KB, exactly what tcgen05.mma reads as its B operand, K-major, no swizzle):
-//   one pass : [4 k-groups][128 n][8 k] 16-bit                    (K = 32: two K=16 steps)
-//   x3       : hi [2 k-groups][128 n][8 k] fp16, then lo likewise (K = 16: one step, hi and lo parts)
+// The stream is the B operand of every MMA of one sample, in issue order, already in the layout
+// tcgen05.mma reads (K-major, no swizzle: [k-group][n][8 k] 16-bit, 8-row x 16-byte core matrices):
+//   one pass : per 32-wide K chunk one stage  [4 k-groups][N][8]                      (N*64 bytes)
+//   x3       : per K=16 step two stages: hi [2 k-groups][N][8] fp16, then lo likewise (N*32 bytes each)
 struct PackSrc {
   const float* w[20];
   GemmLayer g[MAX_GEMM];
   int in_features[MAX_GEMM];
+  long unit_byte0[MAX_UNITS + 1];
 };
 
 template <bool X3, bool BF16>
-__global__ void pack_stream_kernel(Program P, PackSrc src, int kind, uint16_t* __restrict__ out) {
-  const long total = (long)P.n_stages * (STAGE_BYTES / 2);
+__global__ void pack_stream_kernel(Program P, PackSrc src, uint16_t* __restrict__ out) {
+  const long total = P.stream_bytes / 2;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int stage = (int)(idx / (STAGE_BYTES / 2));
-    const int e = (int)(idx % (STAGE_BYTES / 2));
     int ui = 0;
-    while (ui + 1 < P.n_units && P.u[ui + 1].stage0 <= stage) ++ui;
+    while (ui + 1 < P.n_units && src.unit_byte0[ui + 1] <= idx * 2) ++ui;
     const Unit& u = P.u[ui];
-    // locate chunk and sub-stage
-    int rel = stage - u.stage0, c = 0, sub = 0;
+    const int N = u.n128 * 128;
+    const int stage_elems = N * (X3 ? 16 : 32);
+    const long rel = idx - src.unit_byte0[ui] / 2;
+    int stage = (int)(rel / stage_elems);
+    const int e = (int)(rel % stage_elems);
+    int c = 0;
     for (;; ++c) {
-      const int ns = X3 ? (u.chunk[c] == CH_P ? 1 : 2) : 1;
-      if (rel < ns) { sub = rel; break; }
-      rel -= ns;
+      const int ns = chunk_stages(u.ch[c], X3);
+      if (stage < ns) break;
+      stage -= ns;
     }
-    const int id = u.chunk[c];
-    int part = 0, kg, n, kk, kin;
-    if (X3) {
-      part = e / 2048;
-      const int e2 = e % 2048;
-      kg = e2 / 1024; n = (e2 % 1024) / 8; kk = e2 % 8;
-      kin = sub * 16 + kg * 8 + kk;
-    } else {
-      kg = e / 1024; n = (e % 1024) / 8; kk = e % 8;
-      kin = kg * 8 + kk;
-    }
+    const int id = (u.ch[c] >> 16) & 15;
+    const int kg = e / (N * 8), n = (e % (N * 8)) / 8, kk = e % 8;
+    const int part = X3 ? (stage & 1) : 0;
+    const int kin = X3 ? (stage >> 1) * 16 + kg * 8 + kk : kg * 8 + kk;
     const GemmLayer& g = src.g[u.gemm];
-    const int in_features = src.in_features[u.gemm];
     int col = -1;
     if (id < 8) col = id * 32 + kin;
     else {
@@ -171,7 +184,7 @@ __global__ void pack_stream_kernel(Program P, PackSrc src, int kind, uint16_t* _
       if (a < g.aux_cnt) col = g.aux_col0 + a;
     }
     float v = 0.f;
-    if (col >= 0) v = src.w[g.src][(size_t)(u.half * 128 + n) * in_features + col];
+    if (col >= 0) v = src.w[g.src][(size_t)n * src.in_features[u.gemm] + col];
     uint16_t bits;
     if (BF16) {
       bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
@@ -185,28 +198,22 @@ __global__ void pack_stream_kernel(Program P, PackSrc src, int kind, uint16_t* _
 }
 
 // ---- render kernel -----------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;  // 12 warps: producer, MMA issuer, TMEM allocator, (idle), 4 epilogue, 4 encoder
 constexpr int SMEM_MAX = 232448;
 
 template <int KIND, bool X3>
 struct SmemPlan {
-  static constexpr int A = 0;                          // 1-pass: two 64 KB buffers; x3: hi | lo
-  static constexpr int A_LO = 65536;
-  static constexpr int E = 131072;                     // 64-wide encoding (two chunks)
-  static constexpr int E_LO = 16384;
-  static constexpr int V = E + (X3 ? 32768 : 16384);   // 32-wide view encoding
-  static constexpr int V_LO = 8192;
-  static constexpr int P = V + (X3 ? 16384 : 8192);    // raw position (auto-decoder only)
-  static constexpr int P_LO = 4096;
+  static constexpr int P = off_P(X3);
   static constexpr int P_BYTES = KIND == AON_KIND_AUTODECODER ? 8192 : 0;
   static constexpr int PARAMS = P + P_BYTES;           // fp32 biases + head weights
-  static constexpr int PARAM_FLOATS = KIND == AON_KIND_AUTODECODER ? 4400 : 3200;
+  static constexpr int PARAM_FLOATS = KIND == AON_KIND_AUTODECODER ? 4368 : 3088;
   static constexpr int BARS = PARAMS + PARAM_FLOATS * 4;
-  static constexpr int BAR_BYTES = 512;
+  static constexpr int BAR_BYTES = 384;
   static constexpr int RING = (BARS + BAR_BYTES + 127) / 128 * 128;
-  static constexpr int NSTAGE_RAW = (SMEM_MAX - 1024 - RING) / STAGE_BYTES;
-  static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
-  static constexpr int TOTAL = RING + NSTAGE * STAGE_BYTES + 1024;
+  static constexpr int STAGE = X3 ? 8192 : 16384;      // ring slot size (stages of 128-wide layers use half)
+  static constexpr int NSTAGE_RAW = (SMEM_MAX - 1024 - RING) / STAGE;
+  static constexpr int NSTAGE = NSTAGE_RAW > (X3 ? 8 : 6) ? (X3 ? 8 : 6) : NSTAGE_RAW;
+  static constexpr int TOTAL = RING + NSTAGE * STAGE + 1024;
   static_assert(NSTAGE >= 3, "weight ring too small");
 };
 
@@ -225,15 +232,15 @@ struct TcParams {
   float* acc;
   float* depth;
   float* weights;
-  float* dbg;        // optional [n_units][128][128] pre-activation dump of tile 0 / sample 0
+  float* dbg;        // optional [n_units][128][256] pre-activation dump of tile 0 / sample 0
   int* err_flag;     // optional: set to a non-zero code when a barrier wait times out
 };
 
 // barrier slots (8 bytes each) inside the BARS region
-constexpr int BAR_FULL = 0, BAR_EMPTY = 8, BAR_DFULL = 16, BAR_DEMPTY = 20, BAR_CHUNK = 24, BAR_TMEM = 40;
+constexpr int BAR_FULL = 0, BAR_EMPTY = 8, BAR_DFULL = 16, BAR_DEMPTY = 18, BAR_CHUNK = 20, BAR_EFREE = 32,
+              BAR_XW = 33, BAR_TMEM = 40;
 
-__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int* err_flag, int code) {
-  if (ptx::mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void wait_slow(uint32_t bar, uint32_t parity, int* err_flag, int code) {
   const long long t0 = clock64();
   while (!ptx::mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) {  // ~2 s: a schedule bug, not a slow kernel
@@ -243,22 +250,55 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int* err
     }
   }
 }
-
-template <int L>
-__device__ __forceinline__ float enc_val(int k, float x, float y, float z) {
-  // helper.py:136-140: [x y z | sin(2^f v_d), f-major | sin(2^f v_d + pi/2), f-major], then zero padding
-  if (k < 3) return k == 0 ? x : (k == 1 ? y : z);
-  if (k >= 3 + 6 * L) return 0.f;
-  const bool shifted = k >= 3 + 3 * L;
-  const int j = k - 3 - (shifted ? 3 * L : 0);
-  const int f = j / 3, d = j - 3 * f;
-  const float v = d == 0 ? x : (d == 1 ? y : z);
-  const float xb = v * (float)(1 << f);  // exact (power of two)
-  return sinf(shifted ? __fadd_rn(xb, AON_HALF_PI_F) : xb);
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  if (!ptx::mbar_try_wait(bar, parity)) wait_slow(bar, parity, err_flag, code);
 }
 
 template <bool X3, bool BF16>
-__device__ __forceinline__ void pack8(const float (&v)[8], uint4& hi, uint4& lo) {
+__device__ __forceinline__ void split16(float v, uint16_t& hi, uint16_t& lo) {
+  if (BF16) {
+    hi = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    lo = 0;
+  } else {
+    const __half h = __float2half_rn(v);
+    hi = __half_as_ushort(h);
+    lo = X3 ? __half_as_ushort(__float2half_rn(v - __half2float(h))) : (uint16_t)0;
+  }
+}
+
+// element k of row `row` of an operand region lives at base + (k/8)*2048 + row*16 + (k%8)*2
+template <bool X3, bool BF16>
+__device__ __forceinline__ void put16(unsigned char* base, int lo_delta, int row, int k, float v) {
+  uint16_t hi, lo;
+  split16<X3, BF16>(v, hi, lo);
+  unsigned char* p = base + (k >> 3) * 2048 + row * 16 + (k & 7) * 2;
+  *reinterpret_cast<uint16_t*>(p) = hi;
+  if (X3) *reinterpret_cast<uint16_t*>(p + lo_delta) = lo;
+}
+
+// pos_enc (helper.py:136-140) of one point into an operand region of NK columns:
+// [x y z | sin(2^f v_d) f-major | sin(2^f v_d + pi/2) f-major | zero padding]
+template <int L, int NK, bool X3, bool BF16>
+__device__ __forceinline__ void encode_store(unsigned char* base, int lo_delta, int row, float x, float y, float z) {
+  put16<X3, BF16>(base, lo_delta, row, 0, x);
+  put16<X3, BF16>(base, lo_delta, row, 1, y);
+  put16<X3, BF16>(base, lo_delta, row, 2, z);
+#pragma unroll 1
+  for (int f = 0; f < L; ++f) {
+    const float sc = (float)(1 << f);
+    const float v[3] = {x * sc, y * sc, z * sc};  // exact (power of two)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      put16<X3, BF16>(base, lo_delta, row, 3 + 3 * f + d, sinf(v[d]));
+      put16<X3, BF16>(base, lo_delta, row, 3 + 3 * L + 3 * f + d, sinf(__fadd_rn(v[d], AON_HALF_PI_F)));
+    }
+  }
+#pragma unroll
+  for (int k = 3 + 6 * L; k < NK; ++k) put16<X3, BF16>(base, lo_delta, row, k, 0.f);
+}
+
+template <bool X3, bool BF16>
+__device__ __forceinline__ void pack8(const float* v, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -279,22 +319,6 @@ __device__ __forceinline__ void pack8(const float (&v)[8], uint4& hi, uint4& lo)
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// writes NK (multiple of 8) encoded values of one row into an operand region: element k of row r at
-// base + (k/8)*2048 + r*16 + (k%8)*2
-template <int L, int NK, bool X3, bool BF16>
-__device__ __forceinline__ void encode_store(unsigned char* base, int lo_delta, int row, float x, float y, float z) {
-#pragma unroll 1
-  for (int kg = 0; kg < NK / 8; ++kg) {
-    float v[8];
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) v[kk] = enc_val<L>(kg * 8 + kk, x, y, z);
-    uint4 hi, lo;
-    pack8<X3, BF16>(v, hi, lo);
-    *reinterpret_cast<uint4*>(base + kg * 2048 + row * 16) = hi;
-    if (X3) *reinterpret_cast<uint4*>(base + lo_delta + kg * 2048 + row * 16) = lo;
-  }
-}
-
 __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
   // tcgen05.wait::ld with the destination registers as in/out operands so that no use of them can be
   // scheduled above the wait
@@ -307,11 +331,16 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
                : "memory");
 }
 
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo32) {
+  // upper word: SBO = 128 B (>>4 = 8) at bits [32,46), descriptor version 1 at bits [46,48)
+  return ((uint64_t)(8u | (1u << 14)) << 32) | lo32;
+}
+
 template <int KIND, bool X3, bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_constant__ TcParams p) {
   using SP = SmemPlan<KIND, X3>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sm_u32 = ptx::smem_u32(sm);
   float* s_par = reinterpret_cast<float*>(sm + SP::PARAMS);
   const uint32_t bars = sm_u32 + SP::BARS;
@@ -322,12 +351,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   const Program& P = p.prog;
   const int S = p.S;
   constexpr int NSTAGE = SP::NSTAGE;
+  constexpr int E_OFF = off_E(X3), V_OFF = off_V(X3), P_OFF = off_P(X3);
 
   // ---- one-time setup ---------------------------------------------------------------------------------
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(bar(BAR_FULL + i), 1); ptx::mbar_init(bar(BAR_EMPTY + i), 1); }
-    for (int i = 0; i < 4; ++i) { ptx::mbar_init(bar(BAR_DFULL + i), 1); ptx::mbar_init(bar(BAR_DEMPTY + i), 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(BAR_DFULL + i), 1); ptx::mbar_init(bar(BAR_DEMPTY + i), 4); }
     for (int i = 0; i < NUM_CHUNK_IDS; ++i) ptx::mbar_init(bar(BAR_CHUNK + i), 4);
+    ptx::mbar_init(bar(BAR_EFREE), 1);
+    ptx::mbar_init(bar(BAR_XW), 4);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -364,73 +396,132 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   if (warp == 0) {
     // ================================ weight producer ================================
     if (lane == 0) {
-      const long total = (long)S * P.n_stages;
-      int srcs = 0;
-      for (long i = 0; i < total; ++i) {
-        const int slot = (int)(i % NSTAGE);
-        if (i >= NSTAGE) wait_bar(bar(BAR_EMPTY + slot), (uint32_t)((i / NSTAGE - 1) & 1), p.err_flag, 1);
-        ptx::mbar_arrive_expect_tx(bar(BAR_FULL + slot), STAGE_BYTES);
-        ptx::bulk_g2s(sm_u32 + SP::RING + slot * STAGE_BYTES, p.packed + (size_t)srcs * STAGE_BYTES, STAGE_BYTES,
-                      bar(BAR_FULL + slot));
-        if (++srcs == P.n_stages) srcs = 0;
+      uint32_t slot = 0, phase = 0;
+      for (int s = 0; s < S; ++s) {
+        const char* src = p.packed;
+        for (int ui = 0; ui < P.n_units; ++ui) {
+          const Unit& u = P.u[ui];
+          const uint32_t bytes = (uint32_t)unit_stage_bytes(u, X3);
+          int nst = 0;
+          for (int c = 0; c < u.n_chunks; ++c) nst += chunk_stages(u.ch[c], X3);
+          for (int i = 0; i < nst; ++i) {
+            wait_bar(bar(BAR_EMPTY + slot), phase ^ 1, p.err_flag, 1);
+            ptx::mbar_arrive_expect_tx(bar(BAR_FULL + slot), bytes);
+            ptx::bulk_g2s(sm_u32 + SP::RING + slot * SP::STAGE, src, bytes, bar(BAR_FULL + slot));
+            src += bytes;
+            if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      constexpr uint32_t IDESC = ptx::idesc_f16(128, 128, BF16 ? 1 : 0);
-      long g = 0, stage_it = 0;
-      // generations of each operand chunk already known to be complete: a barrier must not be
-      // waited on again for a generation it has moved two phases past (the parity would alias)
-      int seen[NUM_CHUNK_IDS];
-      for (int i = 0; i < NUM_CHUNK_IDS; ++i) seen[i] = 0;
+      constexpr uint32_t IDESC128 = ptx::idesc_f16(128, 128, BF16 ? 1 : 0);
+      constexpr uint32_t IDESC256 = ptx::idesc_f16(128, 256, BF16 ? 1 : 0);
+      constexpr uint32_t A_LBO = (2048u >> 4) << 16;  // A operand: 128 rows x 16 B per k-group
+      const uint32_t base16 = sm_u32 >> 4;
+      const uint32_t ring16 = (sm_u32 + SP::RING) >> 4;
+      uint32_t slot = 0, phase = 0, g = 0;
       for (int s = 0; s < S; ++s) {
         for (int ui = 0; ui < P.n_units; ++ui, ++g) {
           const Unit& u = P.u[ui];
-          const int b = (int)(g & 3);
-          if (g >= 4) wait_bar(bar(BAR_DEMPTY + b), (uint32_t)(((g >> 2) - 1) & 1), p.err_flag, 2);
+          const uint32_t b = g & 1;
+          const uint32_t n128 = u.n128;
+          const uint32_t idesc = n128 == 2 ? IDESC256 : IDESC128;
+          const uint32_t b_lbo = (n128 * 128u) << 16;           // (N * 16 B) >> 4 in the LBO field
+          const uint32_t b_kstep16 = n128 * 256u;               // one K=16 step of B: N * 32 B, >> 4
+          const int n_chunks = u.n_chunks;
+          wait_bar(bar(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1, p.err_flag, 2);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)b * 128u;
+          const uint32_t d_tmem = tmem_base + b * 256u;
           uint32_t accum = 0;
-          for (int c = 0; c < u.n_chunks; ++c) {
-            const int id = u.chunk[c];
-            const int need = s * P.wps[id] + u.gen[c];
-            if (need >= seen[id]) {
-              wait_bar(bar(BAR_CHUNK + id), (uint32_t)(need & 1), p.err_flag, 3);
-              seen[id] = need + 1;
-            }
-            ptx::tc_fence_after();
-            uint32_t a_addr, lo_delta;
-            if (id < 8) { a_addr = sm_u32 + SP::A + (X3 ? 0 : u.in_buf * 65536) + id * 8192; lo_delta = SP::A_LO; }
-            else if (id < CH_V) { a_addr = sm_u32 + SP::E + (id - CH_E0) * 8192; lo_delta = SP::E_LO; }
-            else if (id == CH_V) { a_addr = sm_u32 + SP::V; lo_delta = SP::V_LO; }
-            else { a_addr = sm_u32 + SP::P; lo_delta = SP::P_LO; }
-            const int nst = X3 ? (id == CH_P ? 1 : 2) : 1;
-            for (int st = 0; st < nst; ++st, ++stage_it) {
-              const int slot = (int)(stage_it % NSTAGE);
-              wait_bar(bar(BAR_FULL + slot), (uint32_t)((stage_it / NSTAGE) & 1), p.err_flag, 4);
+          for (int c = 0; c < n_chunks; ++c) {
+            const uint32_t w = u.ch[c];
+            if (w & (1u << 20)) {
+              const uint32_t parity = (((uint32_t)s & (w >> 21)) ^ (w >> 22)) & 1u;
+              wait_bar(bar(BAR_CHUNK + ((w >> 16) & 15)), parity, p.err_flag, 3);
               ptx::tc_fence_after();
-              const uint32_t b_addr = sm_u32 + SP::RING + slot * STAGE_BYTES;
-              if (X3) {
-                const uint64_t a_hi = ptx::smem_desc(a_addr + st * 4096, 2048, 128);
-                const uint64_t a_lo = ptx::smem_desc(a_addr + lo_delta + st * 4096, 2048, 128);
-                const uint64_t b_hi = ptx::smem_desc(b_addr, 2048, 128);
-                const uint64_t b_lo = ptx::smem_desc(b_addr + 4096, 2048, 128);
-                ptx::mma_f16_ss(d_tmem, a_hi, b_hi, IDESC, accum);
-                ptx::mma_f16_ss(d_tmem, a_lo, b_hi, IDESC, 1);
-                ptx::mma_f16_ss(d_tmem, a_hi, b_lo, IDESC, 1);
-              } else {
-                ptx::mma_f16_ss(d_tmem, ptx::smem_desc(a_addr, 2048, 128), ptx::smem_desc(b_addr, 2048, 128), IDESC, accum);
-                ptx::mma_f16_ss(d_tmem, ptx::smem_desc(a_addr + 4096, 2048, 128), ptx::smem_desc(b_addr + 4096, 2048, 128),
-                                IDESC, 1);
+            }
+            const uint32_t a_hi = (base16 + (w & 0xFFFFu)) | A_LBO;
+            const uint32_t ksteps = (w >> 23) & 3;
+            if (X3) {
+              const uint32_t a_lo = a_hi + (((w >> 25) & 31u) << 8);  // (lo offset >> 12) << 12 >> 4
+              for (uint32_t ks = 0; ks < ksteps; ++ks) {
+                wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
+                ptx::tc_fence_after();
+                uint64_t bd = mk_desc((ring16 + slot * (SP::STAGE >> 4)) | b_lbo);
+                ptx::mma_f16_ss(d_tmem, mk_desc(a_hi + ks * 256u), bd, idesc, accum);
+                ptx::mma_f16_ss(d_tmem, mk_desc(a_lo + ks * 256u), bd, idesc, 1);
+                ptx::mma_commit(bar(BAR_EMPTY + slot));
+                if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+                wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
+                ptx::tc_fence_after();
+                bd = mk_desc((ring16 + slot * (SP::STAGE >> 4)) | b_lbo);
+                ptx::mma_f16_ss(d_tmem, mk_desc(a_hi + ks * 256u), bd, idesc, 1);
+                ptx::mma_commit(bar(BAR_EMPTY + slot));
+                if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+                accum = 1;
               }
-              accum = 1;
+            } else {
+              wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
+              ptx::tc_fence_after();
+              const uint32_t bd = (ring16 + slot * (SP::STAGE >> 4)) | b_lbo;
+              ptx::mma_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd), idesc, accum);
+              ptx::mma_f16_ss(d_tmem, mk_desc(a_hi + 256u), mk_desc(bd + b_kstep16), idesc, 1);
               ptx::mma_commit(bar(BAR_EMPTY + slot));
+              if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+              accum = 1;
             }
           }
           ptx::mma_commit(bar(BAR_DFULL + b));
+          if (u.last_e_use) ptx::mma_commit(bar(BAR_EFREE));
         }
       }
+    }
+  } else if (warp >= 8) {
+    // ================================ encoder: sample positions -> operand chunks ================================
+    const int row = tid - 256;
+    const long ray = (long)blockIdx.x * 128 + row;
+    const long rl = ray < p.R ? ray : (long)p.R - 1;
+    const float ox = p.rays_o[3 * rl + 0], oy = p.rays_o[3 * rl + 1], oz = p.rays_o[3 * rl + 2];
+    const float dx = p.rays_d[3 * rl + 0], dy = p.rays_d[3 * rl + 1], dz = p.rays_d[3 * rl + 2];
+    const float* tv = p.t_vals + (p.t_stride ? rl * p.t_stride : 0);
+    auto publish = [&](int id) {
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(BAR_CHUNK + id));
+    };
+    {  // view-direction encoding, once per tile (model.py:174: pos_enc(viewdirs, 0, 4))
+      const float vx = p.viewdirs[3 * rl + 0], vy = p.viewdirs[3 * rl + 1], vz = p.viewdirs[3 * rl + 2];
+      encode_store<4, 32, X3, BF16>(sm + V_OFF, LO_V, row, vx, vy, vz);
+      publish(CH_V);
+    }
+    float t = tv[0];
+    for (int s = 0; s < S; ++s) {
+      const float t_next = (s + 1 < S) ? tv[s + 1] : 0.f;
+      // cast_rays (helper.py:25-26)
+      float ex = __fadd_rn(ox, __fmul_rn(t, dx)), ey = __fadd_rn(oy, __fmul_rn(t, dy)), ez = __fadd_rn(oz, __fmul_rn(t, dz));
+      if (s > 0) wait_bar(bar(BAR_EFREE), (uint32_t)((s - 1) & 1), p.err_flag, 7);
+      if (KIND == AON_KIND_AUTODECODER) {
+        // raw position -> operand chunk P (deformation MLP input; model_autodecoder.py:196-198)
+        constexpr int PK = X3 ? 16 : 32;
+        put16<X3, BF16>(sm + P_OFF, LO_P, row, 0, ex);
+        put16<X3, BF16>(sm + P_OFF, LO_P, row, 1, ey);
+        put16<X3, BF16>(sm + P_OFF, LO_P, row, 2, ez);
+#pragma unroll
+        for (int k = 3; k < PK; ++k) put16<X3, BF16>(sm + P_OFF, LO_P, row, k, 0.f);
+        publish(CH_P);
+        // warped position x' = x + deformation(x), handed over by the epilogue warps as fp32 in the
+        // (by then consumed) P region
+        wait_bar(bar(BAR_XW), (uint32_t)(s & 1), p.err_flag, 8);
+        const float* xw = reinterpret_cast<const float*>(sm + P_OFF);
+        ex = xw[row]; ey = xw[128 + row]; ez = xw[256 + row];
+      }
+      encode_store<10, 64, X3, BF16>(sm + E_OFF, LO_E, row, ex, ey, ez);
+      publish(CH_E0);
+      publish(CH_E0 + 1);
+      t = t_next;
     }
   } else if (warp >= 4) {
     // ================================ epilogue / per-ray state ================================
@@ -445,90 +536,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     const float* tv = p.t_vals + (p.t_stride ? rl * p.t_stride : 0);
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
 
-    auto publish = [&](int id) {  // make this warp's operand stores visible to the MMA (async proxy)
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar(BAR_CHUNK + id));
-    };
-    auto encode_point = [&](float x, float y, float z) {
-      encode_store<10, 64, X3, BF16>(sm + SP::E, SP::E_LO, row, x, y, z);
-      publish(CH_E0);
-      publish(CH_E0 + 1);
-    };
-
     // head weights / biases in shared memory
     constexpr int NBIAS = KIND == AON_KIND_VANILLA ? 2432 : 3328;
     const float* hw_def = s_par + NBIAS;                                             // auto-decoder only
     const float* hw_sig = s_par + NBIAS + (KIND == AON_KIND_AUTODECODER ? 388 : 0);
     const float* hw_rgb = hw_sig + 260;
 
-    {  // view-direction encoding, once per tile (model.py:174: pos_enc(viewdirs, 0, 4))
-      const float vx = p.viewdirs[3 * rl + 0], vy = p.viewdirs[3 * rl + 1], vz = p.viewdirs[3 * rl + 2];
-      encode_store<4, 32, X3, BF16>(sm + SP::V, SP::V_LO, row, vx, vy, vz);
-      publish(CH_V);
-    }
-
     float trans = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cdepth = 0.f, cacc = 0.f;
     float t_cur = tv[0];
-    float px, py, pz;
-    auto sample_point = [&](float t) {  // cast_rays (helper.py:25-26)
-      px = __fadd_rn(ox, __fmul_rn(t, dx));
-      py = __fadd_rn(oy, __fmul_rn(t, dy));
-      pz = __fadd_rn(oz, __fmul_rn(t, dz));
-    };
-    sample_point(t_cur);
-    if (KIND == AON_KIND_VANILLA) encode_point(px, py, pz);
-
-    long g = 0;
+    uint32_t g = 0;
     for (int s = 0; s < S; ++s) {
       const float t_next = (s + 1 < S) ? tv[s + 1] : 0.f;
-      if (KIND == AON_KIND_AUTODECODER) {
-        // raw position -> operand chunk P (deformation MLP input; model_autodecoder.py:196-198)
-        float v[8] = {px, py, pz, 0.f, 0.f, 0.f, 0.f, 0.f};
-        uint4 hi, lo;
-        pack8<X3, BF16>(v, hi, lo);
-        const uint4 z4 = make_uint4(0, 0, 0, 0);
-        constexpr int PG = X3 ? 2 : 4;  // k-groups of the P chunk
-#pragma unroll
-        for (int kg = 0; kg < PG; ++kg) {
-          *reinterpret_cast<uint4*>(sm + SP::P + kg * 2048 + row * 16) = kg == 0 ? hi : z4;
-          if (X3) *reinterpret_cast<uint4*>(sm + SP::P + SP::P_LO + kg * 2048 + row * 16) = kg == 0 ? lo : z4;
-        }
-        publish(CH_P);
-      }
       float sig = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f;  // head accumulators (density; rgb / deformation)
 
       for (int ui = 0; ui < P.n_units; ++ui, ++g) {
         const Unit& u = P.u[ui];
-        const int b = (int)(g & 3);
-        wait_bar(bar(BAR_DFULL + b), (uint32_t)((g >> 2) & 1), p.err_flag, 5);
-        if (u.wait_next) wait_bar(bar(BAR_DFULL + ((b + 1) & 3)), (uint32_t)(((g + 1) >> 2) & 1), p.err_flag, 6);
-        ptx::tc_fence_after();
-        const float* bias = s_par + u.bias_off;
+        const uint32_t b = g & 1;
         const int epi = u.epi;
         const bool relu = u.relu != 0;
+        const int n_out = u.n128 * 4;  // 32-column chunks of this unit's output
+        const float* bias = s_par + u.bias_off;
         if (epi == EPI_RGB || epi == EPI_DEFORM) { h0 = h1 = h2 = 0.f; }
-        const float* hw = epi == EPI_STORE_SIGMA ? hw_sig + u.half * 128 : (epi == EPI_RGB ? hw_rgb : hw_def);
-        unsigned char* out_base = sm + SP::A + (X3 ? 0 : u.out_buf * 65536) + (u.half * 4) * 8192 + row * 16;
+        const float* hw = epi == EPI_STORE_SIGMA ? hw_sig : (epi == EPI_RGB ? hw_rgb : hw_def);
+        unsigned char* out_base = sm + OFF_A + row * 16;
+        wait_bar(bar(BAR_DFULL + b), (g >> 1) & 1, p.err_flag, 5);
+        ptx::tc_fence_after();
+        const uint32_t d_addr = lane_base + b * 256u;
 
         uint32_t r[2][32];
-        ptx::tmem_ld32(lane_base + (uint32_t)(b * 128), r[0]);
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          tmem_ld_wait_dep(r[cc & 1]);
-          if (cc + 1 < 4) ptx::tmem_ld32(lane_base + (uint32_t)(b * 128 + (cc + 1) * 32), r[(cc + 1) & 1]);
+        ptx::tmem_ld32(d_addr, r[0]);
+#pragma unroll 2
+        for (int cc = 0; cc < n_out; ++cc) {
           float v[32];
+          // the two register buffers alternate; written so that all indexing stays static
+          if ((cc & 1) == 0) {
+            tmem_ld_wait_dep(r[0]);
+            if (cc + 1 < n_out) ptx::tmem_ld32(d_addr + (uint32_t)(cc + 1) * 32u, r[1]);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[0][i]);
+          } else {
+            tmem_ld_wait_dep(r[1]);
+            if (cc + 1 < n_out) ptx::tmem_ld32(d_addr + (uint32_t)(cc + 1) * 32u, r[0]);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[1][i]);
+          }
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias + cc * 32 + i);
-            v[i + 0] = __uint_as_float(r[cc & 1][i + 0]) + b4.x;
-            v[i + 1] = __uint_as_float(r[cc & 1][i + 1]) + b4.y;
-            v[i + 2] = __uint_as_float(r[cc & 1][i + 2]) + b4.z;
-            v[i + 3] = __uint_as_float(r[cc & 1][i + 3]) + b4.w;
+            v[i + 0] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
           }
           if (p.dbg != nullptr && blockIdx.x == 0 && s == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) p.dbg[((size_t)ui * 128 + row) * 128 + cc * 32 + i] = v[i];
+            for (int i = 0; i < 32; ++i) p.dbg[((size_t)ui * 128 + row) * 256 + cc * 32 + i] = v[i];
           }
           if (relu) {
 #pragma unroll
@@ -553,18 +612,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
               h2 = fmaf(w2.x, v[i], h2); h2 = fmaf(w2.y, v[i + 1], h2); h2 = fmaf(w2.z, v[i + 2], h2); h2 = fmaf(w2.w, v[i + 3], h2);
             }
           } else {
-            // next layer's A operand: 32 hidden features of this row -> chunk (half*4 + cc)
+            // next layer's A operand: 32 hidden features of this row -> chunk cc
 #pragma unroll
             for (int kg = 0; kg < 4; ++kg) {
-              float w8[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) w8[i] = v[kg * 8 + i];
               uint4 hi, lo;
-              pack8<X3, BF16>(w8, hi, lo);
+              pack8<X3, BF16>(v + kg * 8, hi, lo);
               *reinterpret_cast<uint4*>(out_base + cc * 8192 + kg * 2048) = hi;
-              if (X3) *reinterpret_cast<uint4*>(out_base + SP::A_LO + cc * 8192 + kg * 2048) = lo;
+              if (X3) *reinterpret_cast<uint4*>(out_base + LO_A + cc * 8192 + kg * 2048) = lo;
             }
-            publish(u.half * 4 + cc);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar(BAR_CHUNK + cc));
           }
         }
         // accumulator drained: hand the TMEM buffer back to the MMA issuer
@@ -573,10 +631,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
         if (lane == 0) ptx::mbar_arrive(bar(BAR_DEMPTY + b));
 
         if (KIND == AON_KIND_AUTODECODER && epi == EPI_DEFORM) {
-          // model_autodecoder.py:203: x' = deformation_layer(h) + pos, then pos_enc(x', 0, 10)
+          // model_autodecoder.py:203: x' = deformation_layer(h) + pos  (pos via cast_rays, helper.py:25-26)
           const float* hb = hw_def + 384;
-          const float ex = __fadd_rn(h0 + hb[0], px), ey = __fadd_rn(h1 + hb[1], py), ez = __fadd_rn(h2 + hb[2], pz);
-          encode_point(ex, ey, ez);
+          float* xw = reinterpret_cast<float*>(sm + P_OFF);
+          xw[row] = __fadd_rn(h0 + hb[0], __fadd_rn(ox, __fmul_rn(t_cur, dx)));
+          xw[128 + row] = __fadd_rn(h1 + hb[1], __fadd_rn(oy, __fmul_rn(t_cur, dy)));
+          xw[256 + row] = __fadd_rn(h2 + hb[2], __fadd_rn(oz, __fmul_rn(t_cur, dz)));
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar(BAR_XW));
         }
       }
 
@@ -606,10 +668,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
         if (p.weights && valid) p.weights[ray * S + s] = w;
       }
       t_cur = t_next;
-      if (s + 1 < S) {
-        sample_point(t_cur);
-        if (KIND == AON_KIND_VANILLA) encode_point(px, py, pz);
-      }
     }
 
     if (valid) {
@@ -695,18 +753,23 @@ extern "C" int aon_pack_weights_tc(int kind, int precision, const float* const* 
   (void)packed_bytes;
   const Program P = build_program(kind, precision);
   const PackedLayout L = layout_tc(kind, precision);
+  const int x3 = precision == AON_PREC_TC_F16X3;
   PackSrc src;
   memset(&src, 0, sizeof(src));
   for (int i = 0; i < num_layers(kind); ++i) src.w[i] = w[i];
+  long byte0 = 0;
   for (int i = 0; i < num_gemm(kind); ++i) {
     src.g[i] = gemm_layers(kind)[i];
     src.in_features[i] = layer_shapes(kind)[src.g[i].src][1];
+    src.unit_byte0[i] = byte0;
+    for (int c = 0; c < P.u[i].n_chunks; ++c) byte0 += (long)chunk_stages(P.u[i].ch[c], x3) * unit_stage_bytes(P.u[i], x3);
   }
+  src.unit_byte0[num_gemm(kind)] = byte0;
   uint16_t* out = (uint16_t*)packed;
   const int blocks = 592;
-  if (precision == AON_PREC_TC_F16X3) pack_stream_kernel<true, false><<<blocks, 256, 0, st>>>(P, src, kind, out);
-  else if (precision == AON_PREC_TC_F16) pack_stream_kernel<false, false><<<blocks, 256, 0, st>>>(P, src, kind, out);
-  else pack_stream_kernel<false, true><<<blocks, 256, 0, st>>>(P, src, kind, out);
+  if (precision == AON_PREC_TC_F16X3) pack_stream_kernel<true, false><<<blocks, 256, 0, st>>>(P, src, out);
+  else if (precision == AON_PREC_TC_F16) pack_stream_kernel<false, false><<<blocks, 256, 0, st>>>(P, src, out);
+  else pack_stream_kernel<false, true><<<blocks, 256, 0, st>>>(P, src, out);
   AON_LAUNCH_CHECK();
   return pack_tail(kind, L, w, b, (char*)packed, st);
 }
@@ -721,7 +784,7 @@ extern "C" void aon_debug_set_buffers(float* dbg_dev, int* err_dev) {
 extern "C" int aon_debug_program_info(int kind, int precision, int* n_units, int* n_stages, int* smem_bytes) {
   const Program P = build_program(kind, precision);
   if (n_units) *n_units = P.n_units;
-  if (n_stages) *n_stages = P.n_stages;
+  if (n_stages) *n_stages = (int)(P.stream_bytes / 1024);  // KB of weights streamed per sample
   if (smem_bytes) {
     const bool x3 = precision == AON_PREC_TC_F16X3;
     *smem_bytes = kind == AON_KIND_VANILLA ? (x3 ? SmemPlan<0, true>::TOTAL : SmemPlan<0, false>::TOTAL)

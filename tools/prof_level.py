@@ -1,0 +1,50 @@
+"""Run one render level of the fused kernel on synthetic rays (for ncu captures / quick timing).
+    python tools/prof_level.py [--precision f16x3] [--kind vanilla] [--rays 18944] [--samples 65] [--iters 3]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from aon_b200 import lib as L, nerf, synth
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--precision", default="f16x3")
+    ap.add_argument("--kind", default="vanilla")
+    ap.add_argument("--rays", type=int, default=148 * 128)
+    ap.add_argument("--samples", type=int, default=65)
+    ap.add_argument("--iters", type=int, default=3)
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    prec = L.PRECISIONS[a.precision]
+    sd = synth.make_state_dict(a.kind, 0, True)
+    net = (nerf.NeRF() if a.kind == "vanilla" else nerf.NeRF_AE_Art())
+    net.load_state_dict({k: v for k, v in sd.items() if not k.startswith("code_library.")})
+    net = net.to(dev).eval()
+    kind = net.coarse_mlp.KIND
+    o, d = L.raygen(480, 640, synth.sapien_focal(480), synth.sapien_camera(0), dev)
+    o, d = o[:a.rays].contiguous(), d[:a.rays].contiguous()
+    packed = net._cache["coarse"].get(net.coarse_mlp, prec)
+    folded = None
+    if a.kind != "vanilla":
+        z = torch.zeros(128, device=dev)
+        folded = L.fold_latents(kind, prec, packed, z + 0.01, z - 0.01, torch.zeros(32, device=dev) + 0.02)
+    t = torch.linspace(2.0, 6.0, a.samples, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters + 1)]
+    ev[0].record()
+    for i in range(a.iters):
+        L.render_level(kind, prec, packed, folded, o, d, d, t, True, False)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.iters)]
+    flop = {"vanilla": 1186816, "autodecoder": 1589760}[a.kind] * a.samples * a.rays
+    print("precision %s kind %s rays %d samples %d: ms %s  -> %.1f algorithmic TFLOP/s" %
+          (a.precision, a.kind, a.rays, a.samples, ["%.2f" % m for m in ms], flop / (min(ms) * 1e-3) / 1e12))
+
+
+if __name__ == "__main__":
+    main()
