@@ -234,6 +234,7 @@ struct TcParams {
   float* weights;
   float* dbg;        // optional [n_units][128][256] pre-activation dump of tile 0 / sample 0
   int* err_flag;     // optional: set to a non-zero code when a barrier wait times out
+  long long* tl;     // optional timeline [3 roles][4 samples][MAX_UNITS][4 events] of SM clocks, CTA 0 only
 };
 
 // barrier slots (8 bytes each) inside the BARS region
@@ -392,6 +393,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  const long long t_start = clock64();
+  auto mark = [&](int role, int s, int ui, int ev) {
+    if (p.tl != nullptr && blockIdx.x == 0 && s < 4) p.tl[((role * 4 + s) * MAX_UNITS + ui) * 4 + ev] = clock64() - t_start;
+  };
 
   if (warp == 0) {
     // ================================ weight producer ================================
@@ -434,6 +439,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           const int n_chunks = u.n_chunks;
           wait_bar(bar(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1, p.err_flag, 2);
           ptx::tc_fence_after();
+          mark(0, s, ui, 0);
           const uint32_t d_tmem = tmem_base + b * 256u;
           uint32_t accum = 0;
           for (int c = 0; c < n_chunks; ++c) {
@@ -443,6 +449,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
               wait_bar(bar(BAR_CHUNK + ((w >> 16) & 15)), parity, p.err_flag, 3);
               ptx::tc_fence_after();
             }
+            if (c == 0) mark(0, s, ui, 1);
+            if (c == n_chunks - 1) mark(0, s, ui, 2);
             const uint32_t a_hi = (base16 + (w & 0xFFFFu)) | A_LBO;
             const uint32_t ksteps = (w >> 23) & 3;
             if (X3) {
@@ -476,6 +484,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           }
           ptx::mma_commit(bar(BAR_DFULL + b));
           if (u.last_e_use) ptx::mma_commit(bar(BAR_EFREE));
+          mark(0, s, ui, 3);
         }
       }
     }
@@ -503,6 +512,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
       // cast_rays (helper.py:25-26)
       float ex = __fadd_rn(ox, __fmul_rn(t, dx)), ey = __fadd_rn(oy, __fmul_rn(t, dy)), ez = __fadd_rn(oz, __fmul_rn(t, dz));
       if (s > 0) wait_bar(bar(BAR_EFREE), (uint32_t)((s - 1) & 1), p.err_flag, 7);
+      if (tid == 256) mark(2, s, 0, 0);
       if (KIND == AON_KIND_AUTODECODER) {
         // raw position -> operand chunk P (deformation MLP input; model_autodecoder.py:196-198)
         constexpr int PK = X3 ? 16 : 32;
@@ -521,6 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
       encode_store<10, 64, X3, BF16>(sm + E_OFF, LO_E, row, ex, ey, ez);
       publish(CH_E0);
       publish(CH_E0 + 1);
+      if (tid == 256) mark(2, s, 0, 1);
       t = t_next;
     }
   } else if (warp >= 4) {
@@ -561,6 +572,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
         unsigned char* out_base = sm + OFF_A + row * 16;
         wait_bar(bar(BAR_DFULL + b), (g >> 1) & 1, p.err_flag, 5);
         ptx::tc_fence_after();
+        if (tid == 128) mark(1, s, ui, 0);
         const uint32_t d_addr = lane_base + b * 256u;
 
         uint32_t r[2][32];
@@ -623,8 +635,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar(BAR_CHUNK + cc));
+            if (tid == 128 && cc == 0) mark(1, s, ui, 1);
           }
         }
+        if (tid == 128) mark(1, s, ui, 2);
         // accumulator drained: hand the TMEM buffer back to the MMA issuer
         ptx::tc_fence_before();
         __syncwarp();
@@ -695,6 +709,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
 // ---- host side -------------------------------------------------------------------------------------------
 static float* g_dbg = nullptr;
 static int* g_err = nullptr;
+static long long* g_tl = nullptr;
 
 template <int KIND, bool X3, bool BF16>
 static int launch(const TcParams& p, int grid, cudaStream_t st) {
@@ -727,6 +742,7 @@ int render_level_tc(int kind, int precision, const void* packed, const float* fo
   p.comp_rgb = comp_rgb; p.acc = acc; p.depth = depth; p.weights = weights;
   p.dbg = g_dbg;
   p.err_flag = g_err;
+  p.tl = g_tl;
   const int grid = (R + 127) / 128;
   const bool van = kind == AON_KIND_VANILLA;
   switch (precision) {
@@ -781,6 +797,7 @@ extern "C" void aon_debug_set_buffers(float* dbg_dev, int* err_dev) {
   g_dbg = dbg_dev;
   g_err = err_dev;
 }
+extern "C" void aon_debug_set_timeline(long long* tl_dev) { g_tl = tl_dev; }
 extern "C" int aon_debug_program_info(int kind, int precision, int* n_units, int* n_stages, int* smem_bytes) {
   const Program P = build_program(kind, precision);
   if (n_units) *n_units = P.n_units;

@@ -229,3 +229,12 @@ def debug_set_buffers(dbg: Optional[torch.Tensor], err: Optional[torch.Tensor]) 
     lib.aon_debug_set_buffers.restype = None
     lib.aon_debug_set_buffers.argtypes = [_vp, _vp]
     lib.aon_debug_set_buffers(None if dbg is None else dbg.data_ptr(), None if err is None else err.data_ptr())
+
+
+def debug_set_timeline(tl: Optional[torch.Tensor]) -> None:
+    """tl: CUDA int64 [3,4,18,4] receiving SM-clock timestamps of pipeline events of CTA 0 (roles: MMA
+    issuer, epilogue warp 0, encoder warp 0; first 4 samples; per unit; 4 events)."""
+    lib = load()
+    lib.aon_debug_set_timeline.restype = None
+    lib.aon_debug_set_timeline.argtypes = [_vp]
+    lib.aon_debug_set_timeline(None if tl is None else tl.data_ptr())

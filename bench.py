@@ -314,13 +314,19 @@ def main():
             pass
         tensor_mode = prec != L.PREC_FP32
         if tensor_mode:
-            peak, peak_src = peaks.get("bf16_tflops_sustained", 1375.4), "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+            peak, peak_src = peaks.get("bf16_tflops_sustained", 1400.0), "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured"
             if "bf16_tflops_sustained" not in peaks:
-                peak_src = "fallback of B200_PROFILING.md (no MEASURED_PEAKS.json)"
+                peak_src = "fallback of B200_PROFILING.md (no MEASURED_PEAKS.json): 1.4 PFLOP/s sustained, of fallback"
         else:
             peak, peak_src = 148 * 128 * 2 * 1.965e-3, "fp32 FFMA peak 148 SM x 128 lanes x 2 x 1.965 GHz (CUDA-core mode; not a tensor-pipe number)"
         flop_fine = FLOP_PER_SAMPLE[args.kind] * S1 * R
         achieved = flop_fine / (fine_ms * 1e-3) / 1e12
+        passes = 3 if prec_name == "f16x3" else 1
+        traffic = None
+        try:   # per-launch DRAM bytes of the fine kernel from the committed ncu --set full capture of this command
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_fine_%s_%s.json" % (args.kind, prec_name))))["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -331,7 +337,8 @@ def main():
                     "steps": e2e_steps, "api": "aon_render_image_host (C ABI, pinned host buffers)"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "render_level (fine, %d samples/ray)" % S1, "achieved": achieved,
-                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "mma_passes": passes, "executed_tflops": achieved * passes, "executed_frac": achieved * passes / peak,
                          "peak_source": peak_src, "kernel_ms": fine_ms,
                          "algorithmic_flop_per_launch": flop_fine,
                          "step_share": {"coarse_ms": coarse_ms, "sample_pdf_ms": pdf_ms, "fine_ms": fine_ms}},

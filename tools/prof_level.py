@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--rays", type=int, default=148 * 128)
     ap.add_argument("--samples", type=int, default=65)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--timeline", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     prec = L.PRECISIONS[a.precision]
@@ -42,6 +43,22 @@ def main():
     torch.cuda.synchronize()
     ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.iters)]
     flop = {"vanilla": 1186816, "autodecoder": 1589760}[a.kind] * a.samples * a.rays
+    if a.timeline:
+        tl = torch.zeros(3, 4, 18, 4, dtype=torch.int64, device=dev)
+        L.debug_set_timeline(tl)
+        L.render_level(kind, prec, packed, folded, o, d, d, t, True, False)
+        torch.cuda.synchronize()
+        L.debug_set_timeline(None)
+        tl = tl.cpu()
+        for s in range(1, 3):
+            print("--- sample %d (clocks rel. to kernel start)" % s)
+            print("enc: efree-wait-done %d  E published %d" % (tl[2, s, 0, 0], tl[2, s, 0, 1]))
+            for ui in range(18):
+                if tl[0, s, ui, 3] == 0:
+                    break
+                m, e = tl[0, s, ui], tl[1, s, ui]
+                print("unit %2d  MMA: start %8d chunk0 %8d lastchunk %8d committed %8d | EPI: dfull %8d pub0 %8d done %8d"
+                      % (ui, m[0], m[1], m[2], m[3], e[0], e[1], e[2]))
     print("precision %s kind %s rays %d samples %d: ms %s  -> %.1f algorithmic TFLOP/s" %
           (a.precision, a.kind, a.rays, a.samples, ["%.2f" % m for m in ms], flop / (min(ms) * 1e-3) / 1e12))
 
