@@ -1,0 +1,252 @@
+"""Lightning-surface modules of the reference, re-hosted on the fused kernels.
+
+* ``LitNeRF``             <- models/vanilla_nerf/model.py:202-507
+* ``LitNeRF_AutoDecoder`` <- models/vanilla_nerf/model_autodecoder.py:340-771
+
+Same constructor arguments, hook names and signatures (PL 1.5 ``optimizer_step`` 8-argument form),
+same render dict keys (``comp_rgb / acc / depth``; test: ``target / instance_mask / rgb``) and the same
+``state_dict`` key names (``model.coarse_mlp.pts_linears.0.weight`` ... / ``code_library.*``), so a
+reference checkpoint loads unchanged.  pytorch-lightning is not installed in this image: ``Trainer``
+below is the minimal loop that drives those hooks (one process per GPU; gradients averaged with one
+flat all-reduce, dist.py); the classes stay plain ``nn.Module`` and also work under real PL 1.5.2.
+
+Differences from the reference, all result-preserving:
+* the Python chunk loop of ``render_rays`` / ``render_rays_test`` (model.py:295-348) is gone: the fused
+  kernel never materialises a [rays x samples x features] tensor, so a whole image is one call
+  (``hparams.chunk`` is accepted and ignored; per-ray arithmetic does not depend on the chunking);
+* wandb / image-grid logging is replaced by a ``logged`` dict (no network in the image).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import dist as D
+from .nerf import CodeLibraryArticulated, NeRF, NeRF_AE_Art, img2mse, mse2psnr
+
+Tensor = torch.Tensor
+
+
+def _hp(hparams) -> SimpleNamespace:
+    d = dict(vars(hparams)) if not isinstance(hparams, dict) else dict(hparams)
+    d.setdefault("chunk", 16 * 240)          # opt.py:103
+    d.setdefault("run_max_steps", 100000)
+    d.setdefault("white_back", True)
+    d.setdefault("img_wh", (640, 480))
+    d.setdefault("N_max_objs", 1)
+    d.setdefault("N_obj_code_length", 128)
+    return SimpleNamespace(**d)
+
+
+class LitModel(nn.Module):
+    """models/interface.py:22-62 -- the parts the render path touches (logging + PSNR)."""
+
+    def __init__(self):
+        super().__init__()
+        self.logged: Dict[str, float] = {}
+        self.trainer = SimpleNamespace(global_step=0, is_global_zero=True)
+
+    def log(self, name, value, **_):
+        self.logged[name] = float(value)
+
+    @torch.no_grad()
+    def psnr_legacy(self, pred: Tensor, gt: Tensor) -> Tensor:
+        """interface.py:54-62: clip to [0,1], -10 log10(mse)."""
+        mse = torch.mean((torch.clip(pred, 0, 1) - torch.clip(gt, 0, 1)) ** 2)
+        return -10.0 * torch.log(mse) / np.log(10)
+
+
+class _LitCommon(LitModel):
+    near, far, white_bkgd = 2.0, 6.0, True     # datasets/sapien.py:72-73 constants; setup() may override
+
+    def _init(self, hparams, lr_init, lr_final, lr_delay_steps, lr_delay_mult, randomized):
+        self.hparams = _hp(hparams)
+        self.lr_init, self.lr_final = lr_init, lr_final
+        self.lr_delay_steps, self.lr_delay_mult = lr_delay_steps, lr_delay_mult
+        self.randomized = randomized
+        self.white_bkgd = bool(self.hparams.white_back)
+
+    def setup(self, stage: Optional[str] = None, datasets: Optional[dict] = None) -> None:
+        """The reference builds SapienDataset objects here (model.py:220-254).  Dataset IO is out of the
+        hot-path scope: callers hand in ``datasets={'train':..,'val':..,'test':..}``
+        objects exposing ``near / far / white_back`` like the reference's."""
+        for k, v in (datasets or {}).items():
+            setattr(self, k + "_dataset", v)
+            self.near, self.far = getattr(v, "near", self.near), getattr(v, "far", self.far)
+            self.white_bkgd = getattr(v, "white_back", self.white_bkgd)
+
+    # ---- optimisation (model.py:386-419) ----
+    def configure_optimizers(self):
+        return torch.optim.Adam(params=self.parameters(), lr=self.lr_init, betas=(0.9, 0.999))
+
+    def learning_rate(self, step: int) -> float:
+        if self.lr_delay_steps > 0:
+            delay = self.lr_delay_mult + (1 - self.lr_delay_mult) * np.sin(
+                0.5 * np.pi * np.clip(step / self.lr_delay_steps, 0, 1))
+        else:
+            delay = 1.0
+        t = np.clip(step / self.hparams.run_max_steps, 0, 1)
+        return float(delay * np.exp(np.log(self.lr_init) * (1 - t) + np.log(self.lr_final) * t))
+
+    def optimizer_step(self, epoch, batch_idx, optimizer, optimizer_idx=0, optimizer_closure=None, on_tpu=False,
+                       using_native_amp=False, using_lbfgs=False):
+        lr = self.learning_rate(self.trainer.global_step)
+        for pg in optimizer.param_groups:
+            pg["lr"] = lr
+        optimizer.step(closure=optimizer_closure)
+
+    @staticmethod
+    def _squeeze(batch, keep=()):
+        return {k: (v if (k in keep or not torch.is_tensor(v)) else v.squeeze(0)) for k, v in batch.items()}
+
+    def _losses(self, rendered, target):
+        loss0 = img2mse(rendered[0][0], target)
+        loss1 = img2mse(rendered[1][0], target)
+        self.log("train/psnr1", mse2psnr(loss1.detach()))
+        self.log("train/psnr0", mse2psnr(loss0.detach()))
+        return loss0, loss1
+
+
+class LitNeRF(_LitCommon):
+    def __init__(self, hparams, lr_init: float = 5.0e-4, lr_final: float = 5.0e-6, lr_delay_steps: int = 2500,
+                 lr_delay_mult: float = 0.01, randomized: bool = True):
+        super().__init__()
+        self._init(hparams, lr_init, lr_final, lr_delay_steps, lr_delay_mult, randomized)
+        self.model = NeRF()
+
+    def training_step(self, batch, batch_idx):
+        batch = self._squeeze(batch, keep=("obj_idx",))
+        rendered = self.model(batch, self.randomized, self.white_bkgd, self.near, self.far)
+        loss0, loss1 = self._losses(rendered, batch["target"])
+        loss = loss1 + loss0
+        self.log("train/loss", loss.detach())
+        return loss
+
+    @torch.no_grad()
+    def render_rays(self, batch, batch_idx=0):
+        fine = self.model(batch, False, self.white_bkgd, self.near, self.far)[1]
+        ret = {"comp_rgb": fine[0], "acc": fine[1], "depth": fine[2]}
+        if "target" in batch:
+            self.log("val/psnr", self.psnr_legacy(ret["comp_rgb"], batch["target"]).mean())
+        return ret
+
+    @torch.no_grad()
+    def render_rays_test(self, batch, batch_idx=0):
+        fine = self.model(batch, False, self.white_bkgd, self.near, self.far)[1]
+        return {"target": batch.get("target"), "instance_mask": batch.get("instance_mask"), "rgb": fine[0]}
+
+    def on_validation_start(self):
+        self.random_batch = 0
+
+    def validation_step(self, batch, batch_idx):
+        return self.render_rays(self._squeeze(batch, keep=("obj_idx",)), batch_idx)
+
+    def test_step(self, batch, batch_idx):
+        return self.render_rays_test({k: (v.squeeze() if torch.is_tensor(v) else v) for k, v in batch.items()}, batch_idx)
+
+
+class LitNeRF_AutoDecoder(_LitCommon):
+    def __init__(self, hparams, lr_init: float = 5.0e-4, lr_final: float = 5.0e-6, lr_delay_steps: int = 2500,
+                 lr_delay_mult: float = 0.01, randomized: bool = True):
+        super().__init__()
+        self._init(hparams, lr_init, lr_final, lr_delay_steps, lr_delay_mult, randomized)
+        self.model = NeRF_AE_Art()
+        self.code_library = CodeLibraryArticulated(self.hparams)
+
+    def training_step(self, batch, batch_idx):
+        batch = self._squeeze(batch, keep=("deg", "instance_id", "articulation_id"))
+        latents = self.code_library(batch)
+        rendered = self.model(batch, self.randomized, self.white_bkgd, self.near, self.far, latents)
+        loss0, loss1 = self._losses(rendered, batch["target"])
+        # model_autodecoder.py:456-466: 1e-4 * sum of mean column norms of the three codes
+        reg = 1e-4 * sum(torch.mean(torch.norm(latents[k], dim=0)) for k in ("density", "color", "articulation"))
+        loss = loss1 + loss0 + reg
+        self.log("train/loss", loss.detach())
+        self.log("train/loss/reg", reg.detach())
+        return loss
+
+    @torch.no_grad()
+    def render_rays(self, batch, latents):
+        fine = self.model(batch, False, self.white_bkgd, self.near, self.far, latents)[1]
+        ret = {"comp_rgb": fine[0], "acc": fine[1], "depth": fine[2]}
+        if "target" in batch:
+            self.log("val/psnr", self.psnr_legacy(ret["comp_rgb"], batch["target"]).mean())
+            if "instance_mask" in batch:
+                m = batch["instance_mask"].view(-1, 1).repeat(1, 3).bool()
+                if m.any():
+                    self.log("val/psnr_obj", self.psnr_legacy(ret["comp_rgb"][m], batch["target"][m]).mean())
+        return ret
+
+    @torch.no_grad()
+    def render_rays_test(self, batch, latents):
+        fine = self.model(batch, False, self.white_bkgd, self.near, self.far, latents)[1]
+        return {"target": batch.get("target"), "instance_mask": batch.get("instance_mask"), "rgb": fine[0]}
+
+    def on_validation_start(self):
+        self.random_batch = 0
+
+    def validation_step(self, batch, batch_idx):
+        batch = self._squeeze(batch, keep=("deg", "instance_id", "articulation_id", "img_wh", "src_imgs"))
+        return self.render_rays(batch, self.code_library(batch))
+
+    def test_step(self, batch, batch_idx):
+        batch = self._squeeze(batch, keep=("deg", "instance_id", "articulation_id", "img_wh", "src_imgs"))
+        return self.render_rays_test(batch, self.code_library(batch, is_test=True))
+
+
+def build_system(hparams):
+    """run.py:21-34 dispatch on --exp_type."""
+    exp = getattr(hparams, "exp_type", "vanilla")
+    if exp == "vanilla":
+        return LitNeRF(hparams)
+    if exp == "vanilla_autodecoder":
+        return LitNeRF_AutoDecoder(hparams)
+    raise ValueError("exp_type %r is outside the hot-path scope (SURVEY.md section 2 rows 11-12)" % exp)
+
+
+class Trainer:
+    """Minimal stand-in for ``pl.Trainer(...).fit/test`` (run.py:135-166): drives the hooks above, one
+    process per GPU.  Training gradients are averaged across ranks with ONE flat all-reduce per step
+    (DDP semantics of run.py:109; dist.allreduce_mean_)."""
+
+    def __init__(self, max_steps: int = 1000, log_every: int = 0):
+        self.max_steps, self.log_every = max_steps, log_every
+        self.global_step = 0
+        self.is_global_zero = D.world()[0] == 0
+
+    def fit(self, system: _LitCommon, batches) -> _LitCommon:
+        system.trainer = self
+        opt = system.configure_optimizers()
+        params = [p for p in system.parameters() if p.requires_grad]
+        system.train()
+        for batch_idx, batch in enumerate(batches):
+            if self.global_step >= self.max_steps:
+                break
+            opt.zero_grad(set_to_none=False)
+            loss = system.training_step(batch, batch_idx)
+            loss.backward()
+            if D.world()[1] > 1:
+                flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+                D.allreduce_mean_(flat)
+                off = 0
+                for p in params:
+                    n = p.numel()
+                    if p.grad is not None:
+                        p.grad.copy_(flat[off:off + n].view_as(p))
+                    off += n
+            system.optimizer_step(0, batch_idx, opt, 0, None, False, False, False)
+            self.global_step += 1
+            if self.log_every and self.is_global_zero and self.global_step % self.log_every == 0:
+                print("step %d  %s" % (self.global_step, {k: round(v, 4) for k, v in system.logged.items()}), flush=True)
+        return system
+
+    @torch.no_grad()
+    def test(self, system: _LitCommon, batches) -> list:
+        system.trainer = self
+        system.eval()
+        return [system.test_step(b, i) for i, b in enumerate(batches)]
