@@ -1,7 +1,7 @@
 // render_tc.cu -- tensor-core (tcgen05 / TMEM) version of the fused per-level render kernel.
 //
-// One CTA renders 128 rays.  MMA row m = ray m of the tile, and the CTA walks the S samples of its
-// rays one 128-row "sample plane" at a time, so a ray's transmittance / colour / depth accumulators
+// A CTA PAIR (cluster of 2, tcgen05 cta_group::2) renders 256 rays, 128 per CTA.  MMA row m = ray m of
+// the CTA's tile, and each CTA walks the S samples of its rays one 128-row "sample plane" at a time, so a ray's transmittance / colour / depth accumulators
 // are running scalars in one epilogue thread and no [rays x samples x features] tensor ever reaches
 // HBM (reference: helper.py:25-26,136-140,157-195; model.py:95-120,174-195;
 // model_autodecoder.py:171-239,306-331).
@@ -10,11 +10,16 @@
 // x all K.  K is cut into 32-wide "chunks"; a chunk is either 32 hidden features written by the
 // epilogue of the previous layer (ids 0..7), one half of the 64-wide positional encoding (8, 9), the
 // 32-wide view-direction encoding (10) or the raw sample position of the deformation MLP (11).
-//   warp 0   producer: streams the pre-packed weight stream (8 KB stages, already in the UMMA
-//            canonical K-major layout) from L2 into a shared-memory ring with 1-D bulk copies
-//   warp 1   MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16) into one of four
-//            128-column TMEM accumulators; a K chunk is issued as soon as the epilogue has published
-//            it, so layer l+1 starts while the second half of layer l is still being drained
+//   warp 0   producer: streams THIS CTA's half (N/2 output features) of the pre-packed weight stream
+//            (8 KB stages, already in the UMMA canonical K-major layout) from L2 into a shared-memory
+//            ring with 1-D bulk copies: every SM ingests, stores and feeds to its tensor core only half
+//            of every B tile (cta_group::2 exchanges the halves in hardware), which is what lifts the
+//            M=128,N=256 MMA from 171 cycles (shared-memory operand bound, measured) to the 128-cycle floor
+//   warp 1   leader CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 (M=256 over the pair,
+//            N=256/128, K=16) into one of two 256-column TMEM accumulators of BOTH CTAs; a K chunk is
+//            issued as soon as the epilogues of both CTAs have published it, so layer l+1 starts while
+//            layer l is still being drained.  peer CTA: relay -- forwards "my half of stage s landed" to
+//            the leader's full barrier (mbarrier.try_wait only works on the local CTA)
 //   warps 4-7 epilogue: tcgen05.ld the accumulators (one TMEM lane = one ray = one thread), add
 //            bias, ReLU, convert to the 16-bit operand format and store the next layer's A operand
 //            chunk to shared memory; the 1-/3-wide heads (density, rgb, deformation) are fp32 FMAs
@@ -57,13 +62,16 @@ struct Unit {
 
 struct Program {
   int n_units, n_gemm, x3;
-  long stream_bytes;           // weight stream bytes per sample
+  long stream_bytes;           // weight stream bytes per sample PER CTA of the pair (the blob holds two such halves)
   uint16_t layer_n[MAX_GEMM];  // out features of each GEMM layer (bias vector lengths)
   Unit u[MAX_UNITS];
 };
 
-__host__ __device__ inline int unit_stage_bytes(const Unit& u, int x3) { return u.n128 * 128 * (x3 ? 32 : 64); }
-__host__ __device__ inline int chunk_stages(uint32_t w, int x3) { return x3 ? 2 * (int)((w >> 23) & 3) : 1; }
+// Per-CTA weight stages (each CTA of the pair streams its own N/2 rows of B):
+//   one pass : one stage per 32-wide K chunk   [4 k-groups][N/2][8] 16-bit            = N/2 * 64 bytes
+//   x3       : one stage per K=16 step         hi [2 k-groups][N/2][8], then lo likewise = N/2 * 64 bytes
+__host__ __device__ inline int unit_stage_bytes(const Unit& u, int) { return u.n128 * 4096; }
+__host__ __device__ inline int chunk_stages(uint32_t w, int x3) { return x3 ? (int)((w >> 23) & 3) : 1; }
 
 static Program build_program(int kind, int precision) {
   Program P;
@@ -138,32 +146,34 @@ PackedLayout layout_tc(int kind, int precision) {
   memset(&L, 0, sizeof(L));
   const Program P = build_program(kind, precision);
   for (int i = 0; i < num_gemm(kind); ++i) L.w[i] = 0;  // one contiguous stream in unit order
-  layout_tail(kind, L, (P.stream_bytes + 255) / 256 * 256);
+  layout_tail(kind, L, (2 * P.stream_bytes + 255) / 256 * 256);
   return L;
 }
 
 // ---- weight stream packing ----------------------------------------------------------------------------
-// The stream is the B operand of every MMA of one sample, in issue order, already in the layout
-// tcgen05.mma reads (K-major, no swizzle: [k-group][n][8 k] 16-bit, 8-row x 16-byte core matrices):
-//   one pass : per 32-wide K chunk one stage  [4 k-groups][N][8]                      (N*64 bytes)
-//   x3       : per K=16 step two stages: hi [2 k-groups][N][8] fp16, then lo likewise (N*32 bytes each)
+// The blob holds two streams, one per CTA rank of the pair; stream r is the B operand rows
+// n in [r*N/2, (r+1)*N/2) of every MMA of one sample plane, in issue order, already in the layout
+// tcgen05.mma reads (K-major, no swizzle: [k-group][n][8 k] 16-bit, 8-row x 16-byte core matrices).
 struct PackSrc {
   const float* w[20];
   GemmLayer g[MAX_GEMM];
   int in_features[MAX_GEMM];
-  long unit_byte0[MAX_UNITS + 1];
+  long unit_byte0[MAX_UNITS + 1];   // within one half stream
 };
 
 template <bool X3, bool BF16>
 __global__ void pack_stream_kernel(Program P, PackSrc src, uint16_t* __restrict__ out) {
-  const long total = P.stream_bytes / 2;
+  const long half = P.stream_bytes / 2;   // 16-bit elements per half stream
+  const long total = 2 * half;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int rank = (int)(idx / half);
+    const long hidx = idx % half;
     int ui = 0;
-    while (ui + 1 < P.n_units && src.unit_byte0[ui + 1] <= idx * 2) ++ui;
+    while (ui + 1 < P.n_units && src.unit_byte0[ui + 1] <= hidx * 2) ++ui;
     const Unit& u = P.u[ui];
-    const int N = u.n128 * 128;
-    const int stage_elems = N * (X3 ? 16 : 32);
-    const long rel = idx - src.unit_byte0[ui] / 2;
+    const int NH = u.n128 * 64;
+    const int stage_elems = NH * 32;
+    const long rel = hidx - src.unit_byte0[ui] / 2;
     int stage = (int)(rel / stage_elems);
     const int e = (int)(rel % stage_elems);
     int c = 0;
@@ -173,9 +183,17 @@ __global__ void pack_stream_kernel(Program P, PackSrc src, uint16_t* __restrict_
       stage -= ns;
     }
     const int id = (u.ch[c] >> 16) & 15;
-    const int kg = e / (N * 8), n = (e % (N * 8)) / 8, kk = e % 8;
-    const int part = X3 ? (stage & 1) : 0;
-    const int kin = X3 ? (stage >> 1) * 16 + kg * 8 + kk : kg * 8 + kk;
+    int part = 0, kin, n;
+    if (X3) {
+      part = e / (NH * 16);
+      const int r = e % (NH * 16);
+      kin = stage * 16 + (r / (NH * 8)) * 8 + (r & 7);
+      n = (r % (NH * 8)) >> 3;
+    } else {
+      kin = (e / (NH * 8)) * 8 + (e & 7);
+      n = (e % (NH * 8)) >> 3;
+    }
+    n += rank * NH;
     const GemmLayer& g = src.g[u.gemm];
     int col = -1;
     if (id < 8) col = id * 32 + kin;
@@ -198,8 +216,9 @@ __global__ void pack_stream_kernel(Program P, PackSrc src, uint16_t* __restrict_
 }
 
 // ---- render kernel -----------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 384;  // 12 warps: producer, MMA issuer, TMEM allocator, (idle), 4 epilogue, 4 encoder
+constexpr int TC_THREADS = 384;  // 12 warps: producer, MMA issuer / relay, TMEM allocator, (idle), 4 epilogue, 4 encoder
 constexpr int SMEM_MAX = 232448;
+constexpr int MAX_STAGES = 12;
 
 template <int KIND, bool X3>
 struct SmemPlan {
@@ -210,9 +229,9 @@ struct SmemPlan {
   static constexpr int BARS = PARAMS + PARAM_FLOATS * 4;
   static constexpr int BAR_BYTES = 384;
   static constexpr int RING = (BARS + BAR_BYTES + 127) / 128 * 128;
-  static constexpr int STAGE = X3 ? 8192 : 16384;      // ring slot size (stages of 128-wide layers use half)
+  static constexpr int STAGE = 8192;                   // ring slot size (stages of 128-wide layers use half)
   static constexpr int NSTAGE_RAW = (SMEM_MAX - 1024 - RING) / STAGE;
-  static constexpr int NSTAGE = NSTAGE_RAW > (X3 ? 8 : 6) ? (X3 ? 8 : 6) : NSTAGE_RAW;
+  static constexpr int NSTAGE = NSTAGE_RAW > MAX_STAGES ? MAX_STAGES : NSTAGE_RAW;
   static constexpr int TOTAL = RING + NSTAGE * STAGE + 1024;
   static_assert(NSTAGE >= 3, "weight ring too small");
 };
@@ -238,8 +257,10 @@ struct TcParams {
 };
 
 // barrier slots (8 bytes each) inside the BARS region
-constexpr int BAR_FULL = 0, BAR_EMPTY = 8, BAR_DFULL = 16, BAR_DEMPTY = 18, BAR_CHUNK = 20, BAR_EFREE = 32,
-              BAR_XW = 33, BAR_TMEM = 40;
+constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_DFULL = 2 * MAX_STAGES, BAR_DEMPTY = BAR_DFULL + 2,
+              BAR_CHUNK = BAR_DEMPTY + 2, BAR_EFREE = BAR_CHUNK + NUM_CHUNK_IDS, BAR_XW = BAR_EFREE + 1,
+              BAR_TMEM = BAR_XW + 3;
+static_assert((BAR_TMEM + 1) * 8 <= 384, "barrier region too small");
 
 __device__ __noinline__ void wait_slow(uint32_t bar, uint32_t parity, int* err_flag, int code) {
   const long long t0 = clock64();
@@ -254,7 +275,6 @@ __device__ __noinline__ void wait_slow(uint32_t bar, uint32_t parity, int* err_f
 __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int* err_flag, int code) {
   if (!ptx::mbar_try_wait(bar, parity)) wait_slow(bar, parity, err_flag, code);
 }
-
 template <bool X3, bool BF16>
 __device__ __forceinline__ void split16(float v, uint16_t& hi, uint16_t& lo) {
   if (BF16) {
@@ -349,6 +369,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(sm + SP::BARS + 8 * BAR_TMEM);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = ptx::cluster_ctarank();   // 0 = leader (issues the pair's MMAs), 1 = peer
   const Program& P = p.prog;
   const int S = p.S;
   constexpr int NSTAGE = SP::NSTAGE;
@@ -356,16 +377,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
 
   // ---- one-time setup ---------------------------------------------------------------------------------
   if (tid == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(bar(BAR_FULL + i), 1); ptx::mbar_init(bar(BAR_EMPTY + i), 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(BAR_DFULL + i), 1); ptx::mbar_init(bar(BAR_DEMPTY + i), 4); }
-    for (int i = 0; i < NUM_CHUNK_IDS; ++i) ptx::mbar_init(bar(BAR_CHUNK + i), 4);
+    // leader's FULL: its own producer's arrive.expect_tx + the peer relay's "my half landed" arrive
+    for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(bar(BAR_FULL + i), rank == 0 ? 2 : 1); ptx::mbar_init(bar(BAR_EMPTY + i), 1); }
+    // DEMPTY / CHUNK live in the leader and count the 4 publishing warps of BOTH CTAs
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(BAR_DFULL + i), 1); ptx::mbar_init(bar(BAR_DEMPTY + i), 8); }
+    for (int i = 0; i < NUM_CHUNK_IDS; ++i) ptx::mbar_init(bar(BAR_CHUNK + i), 8);
     ptx::mbar_init(bar(BAR_EFREE), 1);
     ptx::mbar_init(bar(BAR_XW), 4);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(sm_u32 + SP::BARS + 8 * BAR_TMEM, 512);
-    ptx::tmem_relinquish();
+    ptx::tmem_alloc2(sm_u32 + SP::BARS + 8 * BAR_TMEM, 512);
+    ptx::tmem_relinquish2();
   }
   // biases (folded ones for the latent-conditioned layers) and head weights -> shared memory
   {
@@ -390,9 +413,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  ptx::cluster_sync_all();   // barrier inits + TMEM allocation of both CTAs visible before any remote arrive / MMA
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // the leader's CHUNK / DEMPTY / FULL barriers as shared::cluster addresses (valid from either CTA)
+  const uint32_t lead_bars = ptx::mapa(bars, 0);
+  auto lbar = [&](int slot) { return lead_bars + 8u * slot; };
   const long long t_start = clock64();
   auto mark = [&](int role, int s, int ui, int ev) {
     if (p.tl != nullptr && blockIdx.x == 0 && s < 4) p.tl[((role * 4 + s) * MAX_UNITS + ui) * 4 + ev] = clock64() - t_start;
@@ -403,7 +429,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
       for (int s = 0; s < S; ++s) {
-        const char* src = p.packed;
+        const char* src = p.packed + (size_t)rank * P.stream_bytes;
         for (int ui = 0; ui < P.n_units; ++ui) {
           const Unit& u = P.u[ui];
           const uint32_t bytes = (uint32_t)unit_stage_bytes(u, X3);
@@ -420,10 +446,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t IDESC128 = ptx::idesc_f16(128, 128, BF16 ? 1 : 0);
-      constexpr uint32_t IDESC256 = ptx::idesc_f16(128, 256, BF16 ? 1 : 0);
+    if (lane == 0 && rank == 1) {
+      // ================================ peer relay ================================
+      // mbarrier.try_wait is CTA-local, so the leader cannot watch this CTA's FULL barriers: forward each
+      // "my half of the stage landed" to the leader's FULL barrier (count 2) in stage order.
+      uint32_t slot = 0, phase = 0;
+      for (int s = 0; s < S; ++s) {
+        for (int ui = 0; ui < P.n_units; ++ui) {
+          const Unit& u = P.u[ui];
+          int nst = 0;
+          for (int c = 0; c < u.n_chunks; ++c) nst += chunk_stages(u.ch[c], X3);
+          for (int i = 0; i < nst; ++i) {
+            wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 9);
+            ptx::mbar_arrive_cluster(lbar(BAR_FULL + slot));
+            if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (lane == 0) {
+      // ================================ MMA issuer (leader CTA) ================================
+      constexpr uint32_t IDESC128 = ptx::idesc_f16(256, 128, BF16 ? 1 : 0);   // M = 256 over the pair
+      constexpr uint32_t IDESC256 = ptx::idesc_f16(256, 256, BF16 ? 1 : 0);
       constexpr uint32_t A_LBO = (2048u >> 4) << 16;  // A operand: 128 rows x 16 B per k-group
       const uint32_t base16 = sm_u32 >> 4;
       const uint32_t ring16 = (sm_u32 + SP::RING) >> 4;
@@ -434,8 +477,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           const uint32_t b = g & 1;
           const uint32_t n128 = u.n128;
           const uint32_t idesc = n128 == 2 ? IDESC256 : IDESC128;
-          const uint32_t b_lbo = (n128 * 128u) << 16;           // (N * 16 B) >> 4 in the LBO field
-          const uint32_t b_kstep16 = n128 * 256u;               // one K=16 step of B: N * 32 B, >> 4
+          const uint32_t b_lbo = (n128 * 64u) << 16;            // (N/2 rows * 16 B) >> 4 in the LBO field
+          const uint32_t b_kstep16 = n128 * 128u;               // one K=16 step of B: N/2 * 32 B, >> 4
           const int n_chunks = u.n_chunks;
           wait_bar(bar(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1, p.err_flag, 2);
           ptx::tc_fence_after();
@@ -458,16 +501,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
               for (uint32_t ks = 0; ks < ksteps; ++ks) {
                 wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
                 ptx::tc_fence_after();
-                uint64_t bd = mk_desc((ring16 + slot * (SP::STAGE >> 4)) | b_lbo);
-                ptx::mma_f16_ss(d_tmem, mk_desc(a_hi + ks * 256u), bd, idesc, accum);
-                ptx::mma_f16_ss(d_tmem, mk_desc(a_lo + ks * 256u), bd, idesc, 1);
-                ptx::mma_commit(bar(BAR_EMPTY + slot));
-                if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
-                wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
-                ptx::tc_fence_after();
-                bd = mk_desc((ring16 + slot * (SP::STAGE >> 4)) | b_lbo);
-                ptx::mma_f16_ss(d_tmem, mk_desc(a_hi + ks * 256u), bd, idesc, 1);
-                ptx::mma_commit(bar(BAR_EMPTY + slot));
+                const uint32_t bd = (ring16 + slot * (SP::STAGE >> 4)) | b_lbo;   // hi rows; lo rows follow at +N/2*32 B
+                ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + ks * 256u), mk_desc(bd), idesc, accum);
+                ptx::mma2_f16_ss(d_tmem, mk_desc(a_lo + ks * 256u), mk_desc(bd), idesc, 1);
+                ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + ks * 256u), mk_desc(bd + b_kstep16), idesc, 1);
+                ptx::mma_commit2(bar(BAR_EMPTY + slot), 3);
                 if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
                 accum = 1;
               }
@@ -475,15 +513,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
               wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
               ptx::tc_fence_after();
               const uint32_t bd = (ring16 + slot * (SP::STAGE >> 4)) | b_lbo;
-              ptx::mma_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd), idesc, accum);
-              ptx::mma_f16_ss(d_tmem, mk_desc(a_hi + 256u), mk_desc(bd + b_kstep16), idesc, 1);
-              ptx::mma_commit(bar(BAR_EMPTY + slot));
+              ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd), idesc, accum);
+              ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + 256u), mk_desc(bd + b_kstep16), idesc, 1);
+              ptx::mma_commit2(bar(BAR_EMPTY + slot), 3);
               if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
               accum = 1;
             }
           }
-          ptx::mma_commit(bar(BAR_DFULL + b));
-          if (u.last_e_use) ptx::mma_commit(bar(BAR_EFREE));
+          ptx::mma_commit2(bar(BAR_DFULL + b), 3);
+          if (u.last_e_use) ptx::mma_commit2(bar(BAR_EFREE), 3);
           mark(0, s, ui, 3);
         }
       }
@@ -499,7 +537,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     auto publish = [&](int id) {
       ptx::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar(BAR_CHUNK + id));
+      if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_CHUNK + id));
     };
     {  // view-direction encoding, once per tile (model.py:174: pos_enc(viewdirs, 0, 4))
       const float vx = p.viewdirs[3 * rl + 0], vy = p.viewdirs[3 * rl + 1], vz = p.viewdirs[3 * rl + 2];
@@ -634,7 +672,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
             }
             ptx::fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bar(BAR_CHUNK + cc));
+            if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_CHUNK + cc));
             if (tid == 128 && cc == 0) mark(1, s, ui, 1);
           }
         }
@@ -642,7 +680,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
         // accumulator drained: hand the TMEM buffer back to the MMA issuer
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar(BAR_DEMPTY + b));
+        if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_DEMPTY + b));
 
         if (KIND == AON_KIND_AUTODECODER && epi == EPI_DEFORM) {
           // model_autodecoder.py:203: x' = deformation_layer(h) + pos  (pos via cast_rays, helper.py:25-26)
@@ -699,10 +737,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
 
   // ---- teardown ----
   ptx::tc_fence_before();
-  __syncthreads();
+  ptx::cluster_sync_all();   // no CTA of the pair may exit (or free TMEM) while its partner can still touch it
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    ptx::tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -716,7 +754,20 @@ static int launch(const TcParams& p, int grid, cudaStream_t st) {
   using SP = SmemPlan<KIND, X3>;
   auto kern = render_tc_kernel<KIND, X3, BF16>;
   AON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
-  kern<<<grid, TC_THREADS, SP::TOTAL, st>>>(p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = SP::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AON_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
   AON_LAUNCH_CHECK();
   return AON_OK;
 }
@@ -743,7 +794,7 @@ int render_level_tc(int kind, int precision, const void* packed, const float* fo
   p.dbg = g_dbg;
   p.err_flag = g_err;
   p.tl = g_tl;
-  const int grid = (R + 127) / 128;
+  const int grid = ((R + 255) / 256) * 2;   // CTA pairs; an odd last tile leaves the peer with no valid rays
   const bool van = kind == AON_KIND_VANILLA;
   switch (precision) {
     case AON_PREC_TC_F16X3:
