@@ -316,6 +316,9 @@ struct Arena {
 };
 static Arena g_arena;
 
+size_t folded_floats_tc(int kind);                                                            // render_tc.cu
+int fold_stages_tc(int kind, int precision, const PackedLayout& L, float* folded, cudaStream_t st);  // render_tc.cu
+
 }  // namespace aon
 
 using namespace aon;
@@ -381,7 +384,8 @@ int aon_pack_weights(int kind, int precision, const float* const* w, const float
 }
 
 size_t aon_folded_floats(int kind) {
-  return kind == AON_KIND_AUTODECODER ? A_FOLDED_FLOATS + A_LATENT_FLOATS : 0;
+  // fp32 folded biases | latent staging | per-call bias stages of the tensor-core kernel (both CTA ranks)
+  return kind == AON_KIND_AUTODECODER ? folded_floats_tc(kind) : 0;
 }
 
 int aon_fold_latents(int kind, int precision, const void* packed, const float* shape,
@@ -404,6 +408,7 @@ int aon_fold_latents(int kind, int precision, const void* packed, const float* s
         g[i].N, g[i].lat_cnt, lat + g[i].lat_off, folded + L.fold[i]);
     AON_LAUNCH_CHECK();
   }
+  if (precision != AON_PREC_FP32) return fold_stages_tc(kind, precision, L, folded, st);
   return AON_OK;
 }
 

@@ -1,29 +1,34 @@
 // render_tc.cu -- tensor-core (tcgen05 / TMEM) version of the fused per-level render kernel.
 //
 // A CTA PAIR (cluster of 2, tcgen05 cta_group::2) renders 256 rays, 128 per CTA.  MMA row m = ray m of
-// the CTA's tile, and each CTA walks the S samples of its rays one 128-row "sample plane" at a time, so a ray's transmittance / colour / depth accumulators
-// are running scalars in one epilogue thread and no [rays x samples x features] tensor ever reaches
-// HBM (reference: helper.py:25-26,136-140,157-195; model.py:95-120,174-195;
-// model_autodecoder.py:171-239,306-331).
+// the CTA's tile, and each CTA walks the S samples of its rays one 128-row "sample plane" at a time,
+// so a ray's transmittance / colour / depth accumulators are running scalars in one epilogue thread and
+// no [rays x samples x features] tensor ever reaches HBM (reference: helper.py:25-26,136-140,157-195;
+// model.py:95-120,174-195; model_autodecoder.py:171-239,306-331).
 //
-// Work decomposition.  Every nn.Linear with >= 128 outputs is cut into "units": 128 output features
-// x all K.  K is cut into 32-wide "chunks"; a chunk is either 32 hidden features written by the
-// epilogue of the previous layer (ids 0..7), one half of the 64-wide positional encoding (8, 9), the
-// 32-wide view-direction encoding (10) or the raw sample position of the deformation MLP (11).
-//   warp 0   producer: streams THIS CTA's half (N/2 output features) of the pre-packed weight stream
-//            (8 KB stages, already in the UMMA canonical K-major layout) from L2 into a shared-memory
-//            ring with 1-D bulk copies: every SM ingests, stores and feeds to its tensor core only half
-//            of every B tile (cta_group::2 exchanges the halves in hardware), which is what lifts the
-//            M=128,N=256 MMA from 171 cycles (shared-memory operand bound, measured) to the 128-cycle floor
-//   warp 1   leader CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 (M=256 over the pair,
-//            N=256/128, K=16) into one of two 256-column TMEM accumulators of BOTH CTAs; a K chunk is
-//            issued as soon as the epilogues of both CTAs have published it, so layer l+1 starts while
-//            layer l is still being drained.  peer CTA: relay -- forwards "my half of stage s landed" to
-//            the leader's full barrier (mbarrier.try_wait only works on the local CTA)
-//   warps 4-7 epilogue: tcgen05.ld the accumulators (one TMEM lane = one ray = one thread), add
-//            bias, ReLU, convert to the 16-bit operand format and store the next layer's A operand
-//            chunk to shared memory; the 1-/3-wide heads (density, rgb, deformation) are fp32 FMAs
-//            on the fp32 accumulators; then activations + alpha compositing in registers.
+// Work decomposition.  Every nn.Linear with >= 128 outputs is one "unit" (all N outputs x all K).  K is
+// cut into "chunks": 32 hidden features written by the epilogue of the previous layer (ids 0..7), one
+// half of the 64-wide positional encoding (8, 9), the 32-wide view-direction encoding (10), the raw
+// sample position of the deformation MLP (11), or the constant "ones" chunk (12) whose weight rows carry
+// the layer's bias split into three 16-bit pieces -- the bias add happens inside the fp32 accumulation
+// of the tensor core, not in the epilogue.
+//   warp 0     producer: streams THIS CTA's half (N/2 output features) of the pre-packed weight stream
+//              (8 KB stages, already in the UMMA canonical K-major layout) from L2 into a shared-memory
+//              ring with 1-D bulk copies: every SM ingests, stores and feeds to its tensor core only half
+//              of every B tile (cta_group::2 exchanges the halves in hardware), which lifts the
+//              M=128,N=256 MMA from 171 cycles (shared-memory operand bound, measured) to the 128-cycle floor
+//   warp 1     leader CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 (M=256 over the pair,
+//              N=256/128, K=16) into one of two 256-column TMEM accumulators of BOTH CTAs; a K chunk is
+//              issued as soon as the epilogues of both CTAs have published it, so layer l+1 starts while
+//              layer l is still being drained.  peer CTA: relay -- forwards "my half of stage s landed" to
+//              the leader's full barrier (mbarrier.try_wait only works on the local CTA)
+//   warps 2-3  encoder: cast_rays + pos_enc of the next sample (two rays per thread), off the critical path
+//   warps 4-11 epilogue, two warps per TMEM lane quadrant (even / odd 32-column chunks): tcgen05.ld the
+//              accumulators (one TMEM lane = one ray = one thread), ReLU, convert to the 16-bit operand
+//              format and store the next layer's A operand chunk to shared memory; the 1-/3-wide heads
+//              (density, rgb, deformation) are fp32 FMAs on the fp32 accumulators (partial sums of the odd
+//              warp handed to the even warp through shared memory); the even warps own the per-ray state:
+//              activations + alpha compositing in registers.
 // Precision modes: AON_PREC_TC_F16 / _BF16 = one MMA per K step; AON_PREC_TC_F16X3 = operands split
 // into fp16 hi + fp16 lo (about 22 significand bits), three MMAs per K step
 // (hi*hi + lo*hi + hi*lo) with fp32 accumulation -- the mode that meets the 1e-4 parity bar.
@@ -38,16 +43,24 @@ void layout_tail(int kind, PackedLayout& L, int64_t off);  // aon_api.cu
 
 // ---- program (unit schedule), built on the host, passed to the kernels by value ------------------
 constexpr int MAX_UNITS = 18;
-constexpr int MAX_CHUNKS = 10;
-constexpr int CH_E0 = 8, CH_V = 10, CH_P = 11, NUM_CHUNK_IDS = 12;
+constexpr int MAX_CHUNKS = 11;
+constexpr int CH_E0 = 8, CH_V = 10, CH_P = 11, CH_ONE = 12, NUM_CHUNK_IDS = 13;
 enum Epi : int { EPI_STORE = 0, EPI_STORE_SIGMA = 1, EPI_RGB = 2, EPI_DEFORM = 3 };
 
 // shared-memory offsets of the operand regions (bytes from the 1024-aligned base); host and device
 constexpr int OFF_A = 0;
 __host__ __device__ constexpr int off_E(bool x3) { return x3 ? 131072 : 65536; }
 __host__ __device__ constexpr int off_V(bool x3) { return off_E(x3) + (x3 ? 32768 : 16384); }
-__host__ __device__ constexpr int off_P(bool x3) { return off_V(x3) + (x3 ? 16384 : 8192); }
+__host__ __device__ constexpr int off_ONE(bool x3) { return off_V(x3) + (x3 ? 16384 : 8192); }
+__host__ __device__ constexpr int off_P(bool x3) { return off_ONE(x3) + 4096; }
 constexpr int LO_A = 65536, LO_E = 16384, LO_V = 8192, LO_P = 4096;  // hi -> lo part (x3 only)
+
+// Exact power-of-two operand scaling.  fp16 has only 5 exponent bits: the lo part of a hi+lo split of a
+// typical weight (|w| ~ 0.05 -> lo ~ 1e-5) or activation falls into the fp16 subnormal range and loses
+// bits.  Weights are stored as SW*w, activations (every A operand chunk) as SA*a, bias rows as SW*SA*b, so the
+// accumulator holds SW*SA*(W a + b); the epilogue multiplies by 1/SW (exact) and gets SA * pre-activation,
+// i.e. the next layer's scaled operand; the fp32 head weights are pre-divided by SA.
+constexpr float SCALE_W = 64.0f, SCALE_A = 8.0f;
 
 // chunk word: [0,16) operand offset >> 4 | [16,20) chunk id | 20 fresh (first use of a generation: wait)
 //             | 21 writes-per-sample odd | 22 generation parity within a sample | [23,25) K steps of 16
@@ -56,22 +69,29 @@ struct Unit {
   uint8_t gemm, n_chunks, epi, relu;
   uint8_t n128;        // N / 128 (1 or 2)
   uint8_t last_e_use;  // the encoding operand may be overwritten once this unit's MMAs have completed
-  uint16_t bias_off;
+  int16_t fold;        // >= 0: the bias stage comes from the per-call folded buffer, at fold * 16 bytes (per-rank part)
   uint32_t ch[MAX_CHUNKS];
 };
 
 struct Program {
   int n_units, n_gemm, x3;
   long stream_bytes;           // weight stream bytes per sample PER CTA of the pair (the blob holds two such halves)
-  uint16_t layer_n[MAX_GEMM];  // out features of each GEMM layer (bias vector lengths)
+  long fold_half_bytes;        // per-rank size of the folded bias stages (auto-decoder) or 0
   Unit u[MAX_UNITS];
 };
 
 // Per-CTA weight stages (each CTA of the pair streams its own N/2 rows of B):
-//   one pass : one stage per 32-wide K chunk   [4 k-groups][N/2][8] 16-bit            = N/2 * 64 bytes
+//   one pass : one stage per 32-wide K chunk   [4 k-groups][N/2][8] 16-bit              = N/2 * 64 bytes
 //   x3       : one stage per K=16 step         hi [2 k-groups][N/2][8], then lo likewise = N/2 * 64 bytes
-__host__ __device__ inline int unit_stage_bytes(const Unit& u, int) { return u.n128 * 4096; }
-__host__ __device__ inline int chunk_stages(uint32_t w, int x3) { return x3 ? (int)((w >> 23) & 3) : 1; }
+//   bias     : one stage per unit (chunk CH_ONE, K=16) [2 k-groups][N/2][8]              = N/2 * 32 bytes
+__host__ __device__ inline int chunk_id(uint32_t w) { return (int)((w >> 16) & 15u); }
+__host__ __device__ inline int stage_bytes(const Unit& u, uint32_t w) { return (u.n128 * 4096) >> (chunk_id(w) == CH_ONE ? 1 : 0); }
+__host__ __device__ inline int chunk_stages(uint32_t w, int x3) { return (x3 && chunk_id(w) != CH_ONE) ? (int)((w >> 23) & 3) : 1; }
+__host__ __device__ inline long unit_bytes(const Unit& u, int x3) {
+  long b = 0;
+  for (int c = 0; c < u.n_chunks; ++c) b += (long)chunk_stages(u.ch[c], x3) * stage_bytes(u, u.ch[c]);
+  return b;
+}
 
 static Program build_program(int kind, int precision) {
   Program P;
@@ -87,7 +107,8 @@ static Program build_program(int kind, int precision) {
   count[CH_V] = 1;
   struct Use { int ui, c, id, gen; };
   Use uses[MAX_UNITS * MAX_CHUNKS];
-  int n_uses = 0, bias_pref = 0, last_e = -1;
+  int n_uses = 0, last_e = -1;
+  long fold_off = 0;
   for (int gi = 0; gi < ng; ++gi) {
     Unit& u = P.u[gi];
     int epi = EPI_STORE;
@@ -100,8 +121,13 @@ static Program build_program(int kind, int precision) {
       if (gi == 16) epi = EPI_RGB;
     }
     u.gemm = gi; u.epi = epi; u.relu = g[gi].relu; u.n128 = g[gi].N / 128;
-    u.bias_off = (uint16_t)bias_pref;
+    u.fold = -1;
+    if (g[gi].lat_col0 >= 0) {   // latent-conditioned layer: per-call bias stage (aon_fold_latents)
+      u.fold = (int16_t)(fold_off / 16);
+      fold_off += g[gi].N / 2 * 32;
+    }
     int ids[MAX_CHUNKS], nc = 0;
+    ids[nc++] = CH_ONE;          // bias first: needs no activation, so the unit can start at once
     for (int j = 0; j < g[gi].K1 / 32; ++j) ids[nc++] = j;
     if (g[gi].aux == AUX_E) { ids[nc++] = CH_E0; ids[nc++] = CH_E0 + 1; last_e = gi; }
     if (g[gi].aux == AUX_V) ids[nc++] = CH_V;
@@ -111,29 +137,27 @@ static Program build_program(int kind, int precision) {
     if (epi <= EPI_STORE_SIGMA)
       for (int j = 0; j < u.n128 * 4; ++j) count[j]++;
     if (epi == EPI_DEFORM) { count[CH_E0]++; count[CH_E0 + 1]++; }
-    bias_pref += g[gi].N;
   }
+  P.fold_half_bytes = fold_off;
   count[CH_V] = 0;  // written once per CTA: its generation never advances
-  long bytes = 0;
   for (int i = 0; i < n_uses; ++i) {
     const Use& x = uses[i];
     int off, lo;
     if (x.id < 8) { off = OFF_A + x.id * 8192; lo = LO_A; }
     else if (x.id < CH_V) { off = off_E(x3) + (x.id - CH_E0) * 8192; lo = LO_E; }
     else if (x.id == CH_V) { off = off_V(x3); lo = LO_V; }
-    else { off = off_P(x3); lo = LO_P; }
-    const int ksteps = (x3 && x.id == CH_P) ? 1 : 2;
-    const int fresh = x.gen != seen_gen[x.id] || x.id == CH_V;
+    else if (x.id == CH_P) { off = off_P(x3); lo = LO_P; }
+    else { off = off_ONE(x3); lo = 0; }
+    const int ksteps = (x.id == CH_ONE || (x3 && x.id == CH_P)) ? 1 : 2;
+    const int fresh = x.id != CH_ONE && (x.gen != seen_gen[x.id] || x.id == CH_V);
     seen_gen[x.id] = x.gen;
     uint32_t w = (uint32_t)(off >> 4) | ((uint32_t)x.id << 16) | ((uint32_t)fresh << 20) |
                  ((uint32_t)(count[x.id] & 1) << 21) | ((uint32_t)(x.gen & 1) << 22) | ((uint32_t)ksteps << 23) |
                  ((uint32_t)(lo >> 12) << 25);
     P.u[x.ui].ch[x.c] = w;
   }
-  for (int gi = 0; gi < ng; ++gi) {
-    P.layer_n[gi] = (uint16_t)g[gi].N;
-    for (int c = 0; c < P.u[gi].n_chunks; ++c) bytes += (long)chunk_stages(P.u[gi].ch[c], x3) * unit_stage_bytes(P.u[gi], x3);
-  }
+  long bytes = 0;
+  for (int gi = 0; gi < ng; ++gi) bytes += unit_bytes(P.u[gi], x3);
   if (last_e >= 0) P.u[last_e].last_e_use = 1;
   P.n_units = ng;
   P.n_gemm = ng;
@@ -150,16 +174,44 @@ PackedLayout layout_tc(int kind, int precision) {
   return L;
 }
 
+// folded buffer (auto-decoder): [A_FOLDED_FLOATS fp32 biases | A_LATENT_FLOATS staging | bias stages rank 0 | rank 1]
+constexpr int FOLD_STAGE_FLOAT0 = A_FOLDED_FLOATS + A_LATENT_FLOATS;
+size_t folded_floats_tc(int kind) {
+  if (kind != AON_KIND_AUTODECODER) return 0;
+  const Program P = build_program(kind, AON_PREC_TC_F16);
+  return (size_t)FOLD_STAGE_FLOAT0 + (size_t)(2 * P.fold_half_bytes) / 4;
+}
+
 // ---- weight stream packing ----------------------------------------------------------------------------
 // The blob holds two streams, one per CTA rank of the pair; stream r is the B operand rows
 // n in [r*N/2, (r+1)*N/2) of every MMA of one sample plane, in issue order, already in the layout
 // tcgen05.mma reads (K-major, no swizzle: [k-group][n][8 k] 16-bit, 8-row x 16-byte core matrices).
 struct PackSrc {
   const float* w[20];
+  const float* b[20];
   GemmLayer g[MAX_GEMM];
   int in_features[MAX_GEMM];
   long unit_byte0[MAX_UNITS + 1];   // within one half stream
 };
+
+// value -> piece k (0 hi, 1 mid, 2 lo) of its 3-way 16-bit split
+template <bool BF16>
+__device__ __forceinline__ uint16_t split3(float v, int k) {
+  float r = v;
+  uint16_t bits = 0;
+  for (int i = 0; i <= k; ++i) {
+    if (BF16) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(r);
+      bits = __bfloat16_as_ushort(h);
+      r -= __bfloat162float(h);
+    } else {
+      const __half h = __float2half_rn(r);
+      bits = __half_as_ushort(h);
+      r -= __half2float(h);
+    }
+  }
+  return bits;
+}
 
 template <bool X3, bool BF16>
 __global__ void pack_stream_kernel(Program P, PackSrc src, uint16_t* __restrict__ out) {
@@ -172,51 +224,83 @@ __global__ void pack_stream_kernel(Program P, PackSrc src, uint16_t* __restrict_
     while (ui + 1 < P.n_units && src.unit_byte0[ui + 1] <= hidx * 2) ++ui;
     const Unit& u = P.u[ui];
     const int NH = u.n128 * 64;
-    const int stage_elems = NH * 32;
-    const long rel = hidx - src.unit_byte0[ui] / 2;
-    int stage = (int)(rel / stage_elems);
-    const int e = (int)(rel % stage_elems);
-    int c = 0;
-    for (;; ++c) {
-      const int ns = chunk_stages(u.ch[c], X3);
-      if (stage < ns) break;
-      stage -= ns;
-    }
-    const int id = (u.ch[c] >> 16) & 15;
-    int part = 0, kin, n;
-    if (X3) {
-      part = e / (NH * 16);
-      const int r = e % (NH * 16);
-      kin = stage * 16 + (r / (NH * 8)) * 8 + (r & 7);
-      n = (r % (NH * 8)) >> 3;
-    } else {
-      kin = (e / (NH * 8)) * 8 + (e & 7);
-      n = (e % (NH * 8)) >> 3;
-    }
-    n += rank * NH;
     const GemmLayer& g = src.g[u.gemm];
-    int col = -1;
-    if (id < 8) col = id * 32 + kin;
-    else {
-      const int a = (id == CH_E0 + 1 ? 32 : 0) + kin;
-      if (a < g.aux_cnt) col = g.aux_col0 + a;
+    long rel = hidx - src.unit_byte0[ui] / 2;   // element within the unit
+    int c = 0, stage = 0;
+    for (;; ++c) {
+      const long se = stage_bytes(u, u.ch[c]) / 2;
+      const long ce = (long)chunk_stages(u.ch[c], X3) * se;
+      if (rel < ce) { stage = (int)(rel / se); rel -= (long)stage * se; break; }
+      rel -= ce;
     }
-    float v = 0.f;
-    if (col >= 0) v = src.w[g.src][(size_t)n * src.in_features[u.gemm] + col];
+    const int e = (int)rel;
+    const int id = chunk_id(u.ch[c]);
     uint16_t bits;
-    if (BF16) {
-      bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    if (id == CH_ONE) {
+      // bias rows: k = 0,1,2 carry the three pieces of bias[n]; the A side has ones in those columns
+      const int k = (e / (NH * 8)) * 8 + (e & 7);
+      const int n = ((e % (NH * 8)) >> 3) + rank * NH;
+      bits = k < 3 ? split3<BF16>(src.b[g.src][n] * (SCALE_W * SCALE_A), k) : (uint16_t)0;
     } else {
-      const __half hi = __float2half_rn(v);
-      if (X3 && part == 1) bits = __half_as_ushort(__float2half_rn(v - __half2float(hi)));
-      else bits = __half_as_ushort(hi);
+      int part = 0, kin, n;
+      if (X3) {
+        part = e / (NH * 16);
+        const int r = e % (NH * 16);
+        kin = stage * 16 + (r / (NH * 8)) * 8 + (r & 7);
+        n = (r % (NH * 8)) >> 3;
+      } else {
+        kin = (e / (NH * 8)) * 8 + (e & 7);
+        n = (e % (NH * 8)) >> 3;
+      }
+      n += rank * NH;
+      int col = -1;
+      if (id < 8) col = id * 32 + kin;
+      else {
+        const int a = (id == CH_E0 + 1 ? 32 : 0) + kin;
+        if (a < g.aux_cnt) col = g.aux_col0 + a;
+      }
+      float v = 0.f;
+      if (col >= 0) v = src.w[g.src][(size_t)n * src.in_features[u.gemm] + col] * SCALE_W;
+      if (BF16) {
+        bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+      } else {
+        const __half hi = __float2half_rn(v);
+        if (X3 && part == 1) bits = __half_as_ushort(__float2half_rn(v - __half2float(hi)));
+        else bits = __half_as_ushort(hi);
+      }
     }
     out[idx] = bits;
   }
 }
 
+// per-call bias stages of the latent-conditioned layers: folded fp32 biases -> [rank][layer][2 k-groups][N/2][8]
+template <bool BF16>
+__global__ void fold_stage_kernel(Program P, const float* __restrict__ folded, PackedLayout L, uint16_t* __restrict__ out) {
+  for (int ui = 0; ui < P.n_units; ++ui) {
+    const Unit& u = P.u[ui];
+    if (u.fold < 0) continue;
+    const int NH = u.n128 * 64;
+    const float* bias = folded + L.fold[u.gemm];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * NH * 16; idx += gridDim.x * blockDim.x) {
+      const int rank = idx / (NH * 16), e = idx % (NH * 16);
+      const int k = (e / (NH * 8)) * 8 + (e & 7);
+      const int n = ((e % (NH * 8)) >> 3) + rank * NH;
+      out[((size_t)rank * P.fold_half_bytes + (size_t)u.fold * 16) / 2 + e] = k < 3 ? split3<BF16>(bias[n] * (SCALE_W * SCALE_A), k) : (uint16_t)0;
+    }
+  }
+}
+
+int fold_stages_tc(int kind, int precision, const PackedLayout& L, float* folded, cudaStream_t st) {
+  const Program P = build_program(kind, precision);
+  uint16_t* out = reinterpret_cast<uint16_t*>(folded + FOLD_STAGE_FLOAT0);
+  if (precision == AON_PREC_TC_BF16) fold_stage_kernel<true><<<8, 256, 0, st>>>(P, folded, L, out);
+  else fold_stage_kernel<false><<<8, 256, 0, st>>>(P, folded, L, out);
+  AON_LAUNCH_CHECK();
+  return AON_OK;
+}
+
 // ---- render kernel -----------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 384;  // 12 warps: producer, MMA issuer / relay, TMEM allocator, (idle), 4 epilogue, 4 encoder
+constexpr int TC_THREADS = 384;  // 12 warps: producer, MMA issuer / relay, 2 encoder, 8 epilogue
 constexpr int SMEM_MAX = 232448;
 constexpr int MAX_STAGES = 12;
 
@@ -224,12 +308,13 @@ template <int KIND, bool X3>
 struct SmemPlan {
   static constexpr int P = off_P(X3);
   static constexpr int P_BYTES = KIND == AON_KIND_AUTODECODER ? 8192 : 0;
-  static constexpr int PARAMS = P + P_BYTES;           // fp32 biases + head weights
-  static constexpr int PARAM_FLOATS = KIND == AON_KIND_AUTODECODER ? 4368 : 3088;
-  static constexpr int BARS = PARAMS + PARAM_FLOATS * 4;
+  static constexpr int PARAMS = P + P_BYTES;           // fp32 head weights + head biases
+  static constexpr int PARAM_FLOATS = KIND == AON_KIND_AUTODECODER ? 1040 : 648;
+  static constexpr int XCH = PARAMS + PARAM_FLOATS * 4;  // [4][128] fp32 head partial sums (odd -> even epilogue warp)
+  static constexpr int BARS = XCH + 2048;
   static constexpr int BAR_BYTES = 384;
   static constexpr int RING = (BARS + BAR_BYTES + 127) / 128 * 128;
-  static constexpr int STAGE = 8192;                   // ring slot size (stages of 128-wide layers use half)
+  static constexpr int STAGE = 8192;                   // ring slot size (stages of 128-wide layers / bias stages use less)
   static constexpr int NSTAGE_RAW = (SMEM_MAX - 1024 - RING) / STAGE;
   static constexpr int NSTAGE = NSTAGE_RAW > MAX_STAGES ? MAX_STAGES : NSTAGE_RAW;
   static constexpr int TOTAL = RING + NSTAGE * STAGE + 1024;
@@ -259,7 +344,7 @@ struct TcParams {
 // barrier slots (8 bytes each) inside the BARS region
 constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_DFULL = 2 * MAX_STAGES, BAR_DEMPTY = BAR_DFULL + 2,
               BAR_CHUNK = BAR_DEMPTY + 2, BAR_EFREE = BAR_CHUNK + NUM_CHUNK_IDS, BAR_XW = BAR_EFREE + 1,
-              BAR_TMEM = BAR_XW + 3;
+              BAR_TMEM = BAR_XW + 2;
 static_assert((BAR_TMEM + 1) * 8 <= 384, "barrier region too small");
 
 __device__ __noinline__ void wait_slow(uint32_t bar, uint32_t parity, int* err_flag, int code) {
@@ -275,6 +360,7 @@ __device__ __noinline__ void wait_slow(uint32_t bar, uint32_t parity, int* err_f
 __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int* err_flag, int code) {
   if (!ptx::mbar_try_wait(bar, parity)) wait_slow(bar, parity, err_flag, code);
 }
+
 template <bool X3, bool BF16>
 __device__ __forceinline__ void split16(float v, uint16_t& hi, uint16_t& lo) {
   if (BF16) {
@@ -291,31 +377,39 @@ __device__ __forceinline__ void split16(float v, uint16_t& hi, uint16_t& lo) {
 template <bool X3, bool BF16>
 __device__ __forceinline__ void put16(unsigned char* base, int lo_delta, int row, int k, float v) {
   uint16_t hi, lo;
-  split16<X3, BF16>(v, hi, lo);
+  split16<X3, BF16>(v * SCALE_A, hi, lo);
   unsigned char* p = base + (k >> 3) * 2048 + row * 16 + (k & 7) * 2;
   *reinterpret_cast<uint16_t*>(p) = hi;
   if (X3) *reinterpret_cast<uint16_t*>(p + lo_delta) = lo;
 }
 
-// pos_enc (helper.py:136-140) of one point into an operand region of NK columns:
+// pos_enc (helper.py:136-140) of TWO points (rows row and row + 64) into an operand region of NK columns:
 // [x y z | sin(2^f v_d) f-major | sin(2^f v_d + pi/2) f-major | zero padding]
 template <int L, int NK, bool X3, bool BF16>
-__device__ __forceinline__ void encode_store(unsigned char* base, int lo_delta, int row, float x, float y, float z) {
-  put16<X3, BF16>(base, lo_delta, row, 0, x);
-  put16<X3, BF16>(base, lo_delta, row, 1, y);
-  put16<X3, BF16>(base, lo_delta, row, 2, z);
+__device__ __forceinline__ void encode_store2(unsigned char* base, int lo_delta, int row, const float (&x)[2][3]) {
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) put16<X3, BF16>(base, lo_delta, row + 64 * r, d, x[r][d]);
 #pragma unroll 1
   for (int f = 0; f < L; ++f) {
     const float sc = (float)(1 << f);
-    const float v[3] = {x * sc, y * sc, z * sc};  // exact (power of two)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      put16<X3, BF16>(base, lo_delta, row, 3 + 3 * f + d, sinf(v[d]));
-      put16<X3, BF16>(base, lo_delta, row, 3 + 3 * L + 3 * f + d, sinf(__fadd_rn(v[d], AON_HALF_PI_F)));
+      const float v0 = x[0][d] * sc, v1 = x[1][d] * sc;  // exact (power of two)
+      const float s0 = sinf(v0), s1 = sinf(v1);
+      const float c0 = sinf(__fadd_rn(v0, AON_HALF_PI_F)), c1 = sinf(__fadd_rn(v1, AON_HALF_PI_F));
+      put16<X3, BF16>(base, lo_delta, row, 3 + 3 * f + d, s0);
+      put16<X3, BF16>(base, lo_delta, row + 64, 3 + 3 * f + d, s1);
+      put16<X3, BF16>(base, lo_delta, row, 3 + 3 * L + 3 * f + d, c0);
+      put16<X3, BF16>(base, lo_delta, row + 64, 3 + 3 * L + 3 * f + d, c1);
     }
   }
 #pragma unroll
-  for (int k = 3 + 6 * L; k < NK; ++k) put16<X3, BF16>(base, lo_delta, row, k, 0.f);
+  for (int k = 3 + 6 * L; k < NK; ++k) {
+    put16<X3, BF16>(base, lo_delta, row, k, 0.f);
+    put16<X3, BF16>(base, lo_delta, row + 64, k, 0.f);
+  }
 }
 
 template <bool X3, bool BF16>
@@ -357,6 +451,10 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo32) {
   return ((uint64_t)(8u | (1u << 14)) << 32) | lo32;
 }
 
+// named barrier shared by the two epilogue warps of a TMEM lane quadrant (ids 1..4)
+__device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
 template <int KIND, bool X3, bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_constant__ TcParams p) {
   using SP = SmemPlan<KIND, X3>;
@@ -364,6 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   unsigned char* sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sm_u32 = ptx::smem_u32(sm);
   float* s_par = reinterpret_cast<float*>(sm + SP::PARAMS);
+  float* s_xch = reinterpret_cast<float*>(sm + SP::XCH);
   const uint32_t bars = sm_u32 + SP::BARS;
   auto bar = [&](int slot) { return bars + 8u * slot; };
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(sm + SP::BARS + 8 * BAR_TMEM);
@@ -373,15 +472,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   const Program& P = p.prog;
   const int S = p.S;
   constexpr int NSTAGE = SP::NSTAGE;
-  constexpr int E_OFF = off_E(X3), V_OFF = off_V(X3), P_OFF = off_P(X3);
+  constexpr int E_OFF = off_E(X3), V_OFF = off_V(X3), P_OFF = off_P(X3), ONE_OFF = off_ONE(X3);
 
   // ---- one-time setup ---------------------------------------------------------------------------------
   if (tid == 0) {
     // leader's FULL: its own producer's arrive.expect_tx + the peer relay's "my half landed" arrive
     for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(bar(BAR_FULL + i), rank == 0 ? 2 : 1); ptx::mbar_init(bar(BAR_EMPTY + i), 1); }
-    // DEMPTY / CHUNK live in the leader and count the 4 publishing warps of BOTH CTAs
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(BAR_DFULL + i), 1); ptx::mbar_init(bar(BAR_DEMPTY + i), 8); }
-    for (int i = 0; i < NUM_CHUNK_IDS; ++i) ptx::mbar_init(bar(BAR_CHUNK + i), 8);
+    // DEMPTY / CHUNK live in the leader and count the publishing warps of BOTH CTAs: 8 epilogue warps drain an
+    // accumulator, one warp per lane quadrant (4) publishes a hidden chunk, the 2 encoder warps an aux chunk
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(BAR_DFULL + i), 1); ptx::mbar_init(bar(BAR_DEMPTY + i), 16); }
+    for (int i = 0; i < NUM_CHUNK_IDS; ++i) ptx::mbar_init(bar(BAR_CHUNK + i), i < 8 ? 8 : 4);
     ptx::mbar_init(bar(BAR_EFREE), 1);
     ptx::mbar_init(bar(BAR_XW), 4);
     ptx::fence_mbar_init();
@@ -390,27 +490,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     ptx::tmem_alloc2(sm_u32 + SP::BARS + 8 * BAR_TMEM, 512);
     ptx::tmem_relinquish2();
   }
-  // biases (folded ones for the latent-conditioned layers) and head weights -> shared memory
   {
+    // head weights -> shared memory: [deform 3x128 + 4,] density 1x256 + 4, rgb 3x128 + 4 (PackedLayout::head_* order)
     int off = 0;
-    for (int gi = 0; gi < P.n_gemm; ++gi) {
-      const int N = P.layer_n[gi];
-      const float* src = (KIND == AON_KIND_AUTODECODER && p.L.fold[gi] >= 0)
-                             ? p.folded + p.L.fold[gi]
-                             : reinterpret_cast<const float*>(p.packed + p.L.bias[gi]);
-      for (int i = tid; i < N; i += TC_THREADS) s_par[off + i] = src[i];
-      off += N;
-    }
-    // heads: [deform 3x128 + 4,] density 1x256 + 4, rgb 3x128 + 4   (same order as PackedLayout::head_*)
-    constexpr int NH = KIND == AON_KIND_VANILLA ? 2 : 3;
-    for (int h = 0; h < NH; ++h) {
+    constexpr int NHEAD = KIND == AON_KIND_VANILLA ? 2 : 3;
+    for (int h = 0; h < NHEAD; ++h) {
       const int n = (KIND == AON_KIND_AUTODECODER ? (h == 1 ? 256 : 384) : (h == 0 ? 256 : 384));
       const float* w = reinterpret_cast<const float*>(p.packed + p.L.head_w[h]);
       const float* b = reinterpret_cast<const float*>(p.packed + p.L.head_b[h]);
-      for (int i = tid; i < n; i += TC_THREADS) s_par[off + i] = w[i];
+      for (int i = tid; i < n; i += TC_THREADS) s_par[off + i] = w[i] * (1.0f / SCALE_A);
       if (tid < 4) s_par[off + n + tid] = b[tid];
       off += n + 4;
     }
+    // the constant "ones" operand chunk (K=16): columns 0..2 = 1.0 pick up the three bias pieces
+    const uint16_t one = BF16 ? (uint16_t)0x3F80 : (uint16_t)0x3C00;
+    for (int i = tid; i < 128 * 16; i += TC_THREADS) {
+      const int row = i >> 4, k = i & 15;
+      *reinterpret_cast<uint16_t*>(sm + ONE_OFF + (k >> 3) * 2048 + row * 16 + (k & 7) * 2) = k < 3 ? one : (uint16_t)0;
+    }
+    ptx::fence_proxy_async_smem();
   }
   ptx::tc_fence_before();
   ptx::cluster_sync_all();   // barrier inits + TMEM allocation of both CTAs visible before any remote arrive / MMA
@@ -428,19 +526,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     // ================================ weight producer ================================
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
+      const char* fold_src = reinterpret_cast<const char*>(p.folded + FOLD_STAGE_FLOAT0) + (size_t)rank * P.fold_half_bytes;
       for (int s = 0; s < S; ++s) {
         const char* src = p.packed + (size_t)rank * P.stream_bytes;
         for (int ui = 0; ui < P.n_units; ++ui) {
           const Unit& u = P.u[ui];
-          const uint32_t bytes = (uint32_t)unit_stage_bytes(u, X3);
-          int nst = 0;
-          for (int c = 0; c < u.n_chunks; ++c) nst += chunk_stages(u.ch[c], X3);
-          for (int i = 0; i < nst; ++i) {
-            wait_bar(bar(BAR_EMPTY + slot), phase ^ 1, p.err_flag, 1);
-            ptx::mbar_arrive_expect_tx(bar(BAR_FULL + slot), bytes);
-            ptx::bulk_g2s(sm_u32 + SP::RING + slot * SP::STAGE, src, bytes, bar(BAR_FULL + slot));
-            src += bytes;
-            if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+          for (int c = 0; c < u.n_chunks; ++c) {
+            const uint32_t w = u.ch[c];
+            const uint32_t bytes = (uint32_t)stage_bytes(u, w);
+            const int nst = chunk_stages(w, X3);
+            for (int i = 0; i < nst; ++i) {
+              const char* from = src;
+              if (KIND == AON_KIND_AUTODECODER && c == 0 && u.fold >= 0) from = fold_src + (size_t)u.fold * 16;
+              wait_bar(bar(BAR_EMPTY + slot), phase ^ 1, p.err_flag, 1);
+              ptx::mbar_arrive_expect_tx(bar(BAR_FULL + slot), bytes);
+              ptx::bulk_g2s(sm_u32 + SP::RING + slot * SP::STAGE, from, bytes, bar(BAR_FULL + slot));
+              src += bytes;
+              if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -484,15 +587,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           ptx::tc_fence_after();
           mark(0, s, ui, 0);
           const uint32_t d_tmem = tmem_base + b * 256u;
-          uint32_t accum = 0;
-          for (int c = 0; c < n_chunks; ++c) {
+          {  // chunk 0 = bias rows x ones columns: initialises the accumulator (one MMA in every mode)
+            wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
+            ptx::tc_fence_after();
+            const uint32_t bd = (ring16 + slot * (SP::STAGE >> 4)) | b_lbo;
+            ptx::mma2_f16_ss(d_tmem, mk_desc((base16 + (u.ch[0] & 0xFFFFu)) | A_LBO), mk_desc(bd), idesc, 0);
+            ptx::mma_commit2(bar(BAR_EMPTY + slot), 3);
+            if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+          }
+          for (int c = 1; c < n_chunks; ++c) {
             const uint32_t w = u.ch[c];
             if (w & (1u << 20)) {
               const uint32_t parity = (((uint32_t)s & (w >> 21)) ^ (w >> 22)) & 1u;
               wait_bar(bar(BAR_CHUNK + ((w >> 16) & 15)), parity, p.err_flag, 3);
               ptx::tc_fence_after();
             }
-            if (c == 0) mark(0, s, ui, 1);
+            if (c == 1) mark(0, s, ui, 1);
             if (c == n_chunks - 1) mark(0, s, ui, 2);
             const uint32_t a_hi = (base16 + (w & 0xFFFFu)) | A_LBO;
             const uint32_t ksteps = (w >> 23) & 3;
@@ -502,22 +612,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
                 wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
                 ptx::tc_fence_after();
                 const uint32_t bd = (ring16 + slot * (SP::STAGE >> 4)) | b_lbo;   // hi rows; lo rows follow at +N/2*32 B
-                ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + ks * 256u), mk_desc(bd), idesc, accum);
+                ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + ks * 256u), mk_desc(bd), idesc, 1);
                 ptx::mma2_f16_ss(d_tmem, mk_desc(a_lo + ks * 256u), mk_desc(bd), idesc, 1);
                 ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + ks * 256u), mk_desc(bd + b_kstep16), idesc, 1);
                 ptx::mma_commit2(bar(BAR_EMPTY + slot), 3);
                 if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
-                accum = 1;
               }
             } else {
               wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
               ptx::tc_fence_after();
               const uint32_t bd = (ring16 + slot * (SP::STAGE >> 4)) | b_lbo;
-              ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd), idesc, accum);
+              ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd), idesc, 1);
               ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + 256u), mk_desc(bd + b_kstep16), idesc, 1);
               ptx::mma_commit2(bar(BAR_EMPTY + slot), 3);
               if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
-              accum = 1;
             }
           }
           ptx::mma_commit2(bar(BAR_DFULL + b), 3);
@@ -526,56 +634,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp < 4) {
     // ================================ encoder: sample positions -> operand chunks ================================
-    const int row = tid - 256;
-    const long ray = (long)blockIdx.x * 128 + row;
-    const long rl = ray < p.R ? ray : (long)p.R - 1;
-    const float ox = p.rays_o[3 * rl + 0], oy = p.rays_o[3 * rl + 1], oz = p.rays_o[3 * rl + 2];
-    const float dx = p.rays_d[3 * rl + 0], dy = p.rays_d[3 * rl + 1], dz = p.rays_d[3 * rl + 2];
-    const float* tv = p.t_vals + (p.t_stride ? rl * p.t_stride : 0);
+    const int row = tid - 64;   // rows row and row + 64
+    float o[2][3], d[2][3];
+    const float* tv[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const long ray = (long)blockIdx.x * 128 + row + 64 * r;
+      const long rl = ray < p.R ? ray : (long)p.R - 1;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { o[r][k] = p.rays_o[3 * rl + k]; d[r][k] = p.rays_d[3 * rl + k]; }
+      tv[r] = p.t_vals + (p.t_stride ? rl * p.t_stride : 0);
+    }
     auto publish = [&](int id) {
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_CHUNK + id));
     };
     {  // view-direction encoding, once per tile (model.py:174: pos_enc(viewdirs, 0, 4))
-      const float vx = p.viewdirs[3 * rl + 0], vy = p.viewdirs[3 * rl + 1], vz = p.viewdirs[3 * rl + 2];
-      encode_store<4, 32, X3, BF16>(sm + V_OFF, LO_V, row, vx, vy, vz);
+      float v[2][3];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const long ray = (long)blockIdx.x * 128 + row + 64 * r;
+        const long rl = ray < p.R ? ray : (long)p.R - 1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[r][k] = p.viewdirs[3 * rl + k];
+      }
+      encode_store2<4, 32, X3, BF16>(sm + V_OFF, LO_V, row, v);
       publish(CH_V);
     }
-    float t = tv[0];
+    float t[2] = {tv[0][0], tv[1][0]};
     for (int s = 0; s < S; ++s) {
-      const float t_next = (s + 1 < S) ? tv[s + 1] : 0.f;
+      float t_next[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) t_next[r] = (s + 1 < S) ? tv[r][s + 1] : 0.f;
       // cast_rays (helper.py:25-26)
-      float ex = __fadd_rn(ox, __fmul_rn(t, dx)), ey = __fadd_rn(oy, __fmul_rn(t, dy)), ez = __fadd_rn(oz, __fmul_rn(t, dz));
+      float x[2][3];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) x[r][k] = __fadd_rn(o[r][k], __fmul_rn(t[r], d[r][k]));
       if (s > 0) wait_bar(bar(BAR_EFREE), (uint32_t)((s - 1) & 1), p.err_flag, 7);
-      if (tid == 256) mark(2, s, 0, 0);
+      if (tid == 64) mark(2, s, 0, 0);
       if (KIND == AON_KIND_AUTODECODER) {
         // raw position -> operand chunk P (deformation MLP input; model_autodecoder.py:196-198)
         constexpr int PK = X3 ? 16 : 32;
-        put16<X3, BF16>(sm + P_OFF, LO_P, row, 0, ex);
-        put16<X3, BF16>(sm + P_OFF, LO_P, row, 1, ey);
-        put16<X3, BF16>(sm + P_OFF, LO_P, row, 2, ez);
 #pragma unroll
-        for (int k = 3; k < PK; ++k) put16<X3, BF16>(sm + P_OFF, LO_P, row, k, 0.f);
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) put16<X3, BF16>(sm + P_OFF, LO_P, row + 64 * r, k, x[r][k]);
+#pragma unroll
+          for (int k = 3; k < PK; ++k) put16<X3, BF16>(sm + P_OFF, LO_P, row + 64 * r, k, 0.f);
+        }
         publish(CH_P);
         // warped position x' = x + deformation(x), handed over by the epilogue warps as fp32 in the
         // (by then consumed) P region
         wait_bar(bar(BAR_XW), (uint32_t)(s & 1), p.err_flag, 8);
         const float* xw = reinterpret_cast<const float*>(sm + P_OFF);
-        ex = xw[row]; ey = xw[128 + row]; ez = xw[256 + row];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) x[r][k] = xw[128 * k + row + 64 * r];
       }
-      encode_store<10, 64, X3, BF16>(sm + E_OFF, LO_E, row, ex, ey, ez);
+      encode_store2<10, 64, X3, BF16>(sm + E_OFF, LO_E, row, x);
       publish(CH_E0);
       publish(CH_E0 + 1);
-      if (tid == 256) mark(2, s, 0, 1);
-      t = t_next;
+      if (tid == 64) mark(2, s, 0, 1);
+      t[0] = t_next[0]; t[1] = t_next[1];
     }
-  } else if (warp >= 4) {
+  } else {
     // ================================ epilogue / per-ray state ================================
-    const int row = tid - 128;            // ray within the tile == TMEM lane
-    const int quad = warp & 3;            // TMEM lane quadrant of this warp
+    const int quad = warp & 3;              // TMEM lane quadrant of this warp
+    const int half = (warp - 4) >> 2;       // 0: even chunks + owner of the per-ray state; 1: odd chunks
+    const int row = quad * 32 + lane;       // ray within the tile == TMEM lane
+    const bool owner = half == 0;
     const long ray = (long)blockIdx.x * 128 + row;
     const bool valid = ray < p.R;
     const long rl = valid ? ray : (long)p.R - 1;
@@ -586,9 +719,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
 
     // head weights / biases in shared memory
-    constexpr int NBIAS = KIND == AON_KIND_VANILLA ? 2432 : 3328;
-    const float* hw_def = s_par + NBIAS;                                             // auto-decoder only
-    const float* hw_sig = s_par + NBIAS + (KIND == AON_KIND_AUTODECODER ? 388 : 0);
+    const float* hw_def = s_par;                                             // auto-decoder only
+    const float* hw_sig = s_par + (KIND == AON_KIND_AUTODECODER ? 388 : 0);
     const float* hw_rgb = hw_sig + 260;
 
     float trans = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cdepth = 0.f, cacc = 0.f;
@@ -603,41 +735,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
         const uint32_t b = g & 1;
         const int epi = u.epi;
         const bool relu = u.relu != 0;
-        const int n_out = u.n128 * 4;  // 32-column chunks of this unit's output
-        const float* bias = s_par + u.bias_off;
+        const int n_mine = u.n128 * 2;  // my 32-column chunks of this unit's output: cc = 2 j + half
         if (epi == EPI_RGB || epi == EPI_DEFORM) { h0 = h1 = h2 = 0.f; }
         const float* hw = epi == EPI_STORE_SIGMA ? hw_sig : (epi == EPI_RGB ? hw_rgb : hw_def);
         unsigned char* out_base = sm + OFF_A + row * 16;
         wait_bar(bar(BAR_DFULL + b), (g >> 1) & 1, p.err_flag, 5);
         ptx::tc_fence_after();
         if (tid == 128) mark(1, s, ui, 0);
-        const uint32_t d_addr = lane_base + b * 256u;
+        const uint32_t d_addr = lane_base + b * 256u + (uint32_t)half * 32u;
 
         uint32_t r[2][32];
         ptx::tmem_ld32(d_addr, r[0]);
 #pragma unroll 2
-        for (int cc = 0; cc < n_out; ++cc) {
+        for (int j = 0; j < n_mine; ++j) {
+          const int cc = 2 * j + half;
           float v[32];
           // the two register buffers alternate; written so that all indexing stays static
-          if ((cc & 1) == 0) {
+          if ((j & 1) == 0) {
             tmem_ld_wait_dep(r[0]);
-            if (cc + 1 < n_out) ptx::tmem_ld32(d_addr + (uint32_t)(cc + 1) * 32u, r[1]);
+            if (j + 1 < n_mine) ptx::tmem_ld32(d_addr + (uint32_t)(j + 1) * 64u, r[1]);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[0][i]);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[0][i]) * (1.0f / SCALE_W);
           } else {
             tmem_ld_wait_dep(r[1]);
-            if (cc + 1 < n_out) ptx::tmem_ld32(d_addr + (uint32_t)(cc + 1) * 32u, r[0]);
+            if (j + 1 < n_mine) ptx::tmem_ld32(d_addr + (uint32_t)(j + 1) * 64u, r[0]);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[1][i]);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[1][i]) * (1.0f / SCALE_W);
           }
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias + cc * 32 + i);
-            v[i + 0] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          if (j == n_mine - 1) {
+            // accumulator drained (my part): hand the TMEM buffer back to the MMA issuer
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_DEMPTY + b));
           }
           if (p.dbg != nullptr && blockIdx.x == 0 && s == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) p.dbg[((size_t)ui * 128 + row) * 256 + cc * 32 + i] = v[i];
+            for (int i = 0; i < 32; ++i) p.dbg[((size_t)ui * 128 + row) * 256 + cc * 32 + i] = v[i] * (1.0f / SCALE_A);
           }
           if (relu) {
 #pragma unroll
@@ -673,16 +806,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_CHUNK + cc));
-            if (tid == 128 && cc == 0) mark(1, s, ui, 1);
+            if (tid == 128 && j == 0) mark(1, s, ui, 1);
           }
         }
         if (tid == 128) mark(1, s, ui, 2);
-        // accumulator drained: hand the TMEM buffer back to the MMA issuer
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_DEMPTY + b));
 
-        if (KIND == AON_KIND_AUTODECODER && epi == EPI_DEFORM) {
+        // head partial sums of the odd warp -> even warp (owner of the per-ray state)
+        if (epi != EPI_STORE) {
+          if (!owner) {
+            if (epi == EPI_STORE_SIGMA) s_xch[row] = sig;
+            else { s_xch[128 + row] = h0; s_xch[256 + row] = h1; s_xch[384 + row] = h2; }
+            __threadfence_block();
+            pair_bar_arrive(1 + quad);
+          } else {
+            pair_bar_sync(1 + quad);
+            if (epi == EPI_STORE_SIGMA) sig += s_xch[row];
+            else { h0 += s_xch[128 + row]; h1 += s_xch[256 + row]; h2 += s_xch[384 + row]; }
+          }
+        }
+
+        if (KIND == AON_KIND_AUTODECODER && epi == EPI_DEFORM && owner) {
           // model_autodecoder.py:203: x' = deformation_layer(h) + pos  (pos via cast_rays, helper.py:25-26)
           const float* hb = hw_def + 384;
           float* xw = reinterpret_cast<float*>(sm + P_OFF);
@@ -695,7 +838,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
       }
 
       // ---- activations + alpha compositing of sample s (helper.py:157-195) ----
-      {
+      if (owner) {
         const float raw_sigma = sig + hw_sig[256];
         const float* hb = hw_rgb + 384;
         float rr = h0 + hb[0], gg = h1 + hb[1], bb = h2 + hb[2];
@@ -722,7 +865,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
       t_cur = t_next;
     }
 
-    if (valid) {
+    if (valid && owner) {
       if (isnan(cdepth)) cdepth = INFINITY;  // helper.py:179 nan_to_num(depth, nan=inf)
       else if (isinf(cdepth)) cdepth = cdepth > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
       if (p.white_bkgd) {
@@ -823,13 +966,13 @@ extern "C" int aon_pack_weights_tc(int kind, int precision, const float* const* 
   const int x3 = precision == AON_PREC_TC_F16X3;
   PackSrc src;
   memset(&src, 0, sizeof(src));
-  for (int i = 0; i < num_layers(kind); ++i) src.w[i] = w[i];
+  for (int i = 0; i < num_layers(kind); ++i) { src.w[i] = w[i]; src.b[i] = b[i]; }
   long byte0 = 0;
   for (int i = 0; i < num_gemm(kind); ++i) {
     src.g[i] = gemm_layers(kind)[i];
     src.in_features[i] = layer_shapes(kind)[src.g[i].src][1];
     src.unit_byte0[i] = byte0;
-    for (int c = 0; c < P.u[i].n_chunks; ++c) byte0 += (long)chunk_stages(P.u[i].ch[c], x3) * unit_stage_bytes(P.u[i], x3);
+    byte0 += unit_bytes(P.u[i], x3);
   }
   src.unit_byte0[num_gemm(kind)] = byte0;
   uint16_t* out = (uint16_t*)packed;
@@ -852,7 +995,7 @@ extern "C" void aon_debug_set_timeline(long long* tl_dev) { g_tl = tl_dev; }
 extern "C" int aon_debug_program_info(int kind, int precision, int* n_units, int* n_stages, int* smem_bytes) {
   const Program P = build_program(kind, precision);
   if (n_units) *n_units = P.n_units;
-  if (n_stages) *n_stages = (int)(P.stream_bytes / 1024);  // KB of weights streamed per sample
+  if (n_stages) *n_stages = (int)(P.stream_bytes / 1024);  // KB of weights streamed per sample per CTA
   if (smem_bytes) {
     const bool x3 = precision == AON_PREC_TC_F16X3;
     *smem_bytes = kind == AON_KIND_VANILLA ? (x3 ? SmemPlan<0, true>::TOTAL : SmemPlan<0, false>::TOTAL)

@@ -33,7 +33,7 @@ def test_introspection(built_lib):
     assert built_lib.layer_shapes(1) == [(o, i) for _, o, i in O.AUTODECODER_LAYERS]
     assert lib.aon_packed_bytes(0, 0) > 4 * 593408 and lib.aon_packed_bytes(1, 0) > 4 * 600000
     assert lib.aon_packed_bytes(0, 99) == 0
-    assert lib.aon_folded_floats(0) == 0 and lib.aon_folded_floats(1) == 768 + 288
+    assert lib.aon_folded_floats(0) == 0 and lib.aon_folded_floats(1) == 768 + 288 + 6144   # fp32 biases | latents | per-call bias stages (2 ranks)
 
 
 def test_argument_errors_return_codes(built_lib):

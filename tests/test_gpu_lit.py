@@ -29,12 +29,14 @@ def test_lit_eval_and_train(built_lib, exp):
     if exp == "vanilla":
         ret = s.render_rays(batch)
         out = s.test_step({k: (v[None] if torch.is_tensor(v) else v) for k, v in batch.items()}, 0)
-        direct = s.model(batch, False, True, 2.0, 6.0)[1][0]
+        with torch.no_grad():
+            direct = s.model(batch, False, True, 2.0, 6.0)[1][0]
     else:
         lat = s.code_library(batch)
         ret = s.render_rays(batch, lat)
         out = s.render_rays_test(batch, lat)
-        direct = s.model(batch, False, True, 2.0, 6.0, lat)[1][0]
+        with torch.no_grad():
+            direct = s.model(batch, False, True, 2.0, 6.0, lat)[1][0]
     assert set(ret) == {"comp_rgb", "acc", "depth"} and set(out) == {"target", "instance_mask", "rgb"}
     assert torch.equal(ret["comp_rgb"], direct) and torch.equal(out["rgb"], direct)
     assert "val/psnr" in s.logged
