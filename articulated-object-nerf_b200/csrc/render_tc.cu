@@ -12,18 +12,18 @@
 // sample position of the deformation MLP (11), or the constant "ones" chunk (12) whose weight rows carry
 // the layer's bias split into three 16-bit pieces -- the bias add happens inside the fp32 accumulation
 // of the tensor core, not in the epilogue.
-//   warp 0     producer: streams THIS CTA's half (N/2 output features) of the pre-packed weight stream
+//   warp 12    producer: streams THIS CTA's half (N/2 output features) of the pre-packed weight stream
 //              (8 KB stages, already in the UMMA canonical K-major layout) from L2 into a shared-memory
 //              ring with 1-D bulk copies: every SM ingests, stores and feeds to its tensor core only half
 //              of every B tile (cta_group::2 exchanges the halves in hardware), which lifts the
 //              M=128,N=256 MMA from 171 cycles (shared-memory operand bound, measured) to the 128-cycle floor
-//   warp 1     leader CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 (M=256 over the pair,
+//   warps 13,14 leader CTA: MMA issuers -- two threads (alternate weight stages) issue tcgen05.mma.cta_group::2 (M=256 over the pair,
 //              N=256/128, K=16) into one of two 256-column TMEM accumulators of BOTH CTAs; a K chunk is
 //              issued as soon as the epilogues of both CTAs have published it, so layer l+1 starts while
 //              layer l is still being drained.  peer CTA: relay -- forwards "my half of stage s landed" to
 //              the leader's full barrier (mbarrier.try_wait only works on the local CTA)
-//   warps 2-3  encoder: cast_rays + pos_enc of the next sample (two rays per thread), off the critical path
-//   warps 4-11 epilogue, two warps per TMEM lane quadrant (even / odd 32-column chunks): tcgen05.ld the
+//   warps 8-11 encoder: cast_rays + pos_enc of the next sample (one ray per thread), off the critical path
+//   warps 0-7  epilogue, two warps per TMEM lane quadrant (even / odd 32-column chunks): tcgen05.ld the
 //              accumulators (one TMEM lane = one ray = one thread), ReLU, convert to the 16-bit operand
 //              format and store the next layer's A operand chunk to shared memory; the 1-/3-wide heads
 //              (density, rgb, deformation) are fp32 FMAs on the fp32 accumulators (partial sums of the odd
@@ -69,6 +69,7 @@ struct Unit {
   uint8_t gemm, n_chunks, epi, relu;
   uint8_t n128;        // N / 128 (1 or 2)
   uint8_t last_e_use;  // the encoding operand may be overwritten once this unit's MMAs have completed
+  uint8_t n_hidden;    // number of 32-wide hidden input chunks (K1 / 32): chunk list entries 1 .. n_hidden
   int16_t fold;        // >= 0: the bias stage comes from the per-call folded buffer, at fold * 16 bytes (per-rank part)
   uint32_t ch[MAX_CHUNKS];
 };
@@ -121,6 +122,7 @@ static Program build_program(int kind, int precision) {
       if (gi == 16) epi = EPI_RGB;
     }
     u.gemm = gi; u.epi = epi; u.relu = g[gi].relu; u.n128 = g[gi].N / 128;
+    u.n_hidden = (uint8_t)(g[gi].K1 / 32);
     u.fold = -1;
     if (g[gi].lat_col0 >= 0) {   // latent-conditioned layer: per-call bias stage (aon_fold_latents)
       u.fold = (int16_t)(fold_off / 16);
@@ -300,7 +302,12 @@ int fold_stages_tc(int kind, int precision, const PackedLayout& L, float* folded
 }
 
 // ---- render kernel -----------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 384;  // 12 warps: producer, MMA issuer / relay, 2 encoder, 8 epilogue
+constexpr int TC_THREADS = 512;  // 16 warps = 4 warpgroups: 0-7 epilogue | 8-11 encoder | 12 producer, 13 MMA issuer B, 14 MMA issuer A / relay, 15 idle.
+// 512 threads start with 128 registers each; setmaxnreg moves registers from the light warpgroups to the epilogue:
+// 256 x 184 + 128 x 96 + 128 x 48 = 65536.
+constexpr int REGS_EPILOGUE = 176, REGS_ENCODER = 96, REGS_CONTROL = 56;
+// The warp scheduler favours the highest warp id of a sub-partition (measured, B300_MICROARCH.md): the two
+// single-thread latency-critical roles sit above the ALU-heavy epilogue warps that share their sub-partitions.
 constexpr int SMEM_MAX = 232448;
 constexpr int MAX_STAGES = 12;
 
@@ -347,7 +354,7 @@ constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_DFULL = 2 * MAX_STAGES, 
               BAR_TMEM = BAR_XW + 2;
 static_assert((BAR_TMEM + 1) * 8 <= 384, "barrier region too small");
 
-__device__ __noinline__ void wait_slow(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+__device__ __forceinline__ void wait_slow(uint32_t bar, uint32_t parity, int* err_flag, int code) {
   const long long t0 = clock64();
   while (!ptx::mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) {  // ~2 s: a schedule bug, not a slow kernel
@@ -383,33 +390,38 @@ __device__ __forceinline__ void put16(unsigned char* base, int lo_delta, int row
   if (X3) *reinterpret_cast<uint16_t*>(p + lo_delta) = lo;
 }
 
-// pos_enc (helper.py:136-140) of TWO points (rows row and row + 64) into an operand region of NK columns:
+// pos_enc (helper.py:136-140) of NR points (rows row + 32 r) into an operand region of NK columns:
 // [x y z | sin(2^f v_d) f-major | sin(2^f v_d + pi/2) f-major | zero padding]
+constexpr int ENC_ROWS = 1;   // rows per encoder thread (four encoder warps cover the 128-row tile)
 template <int L, int NK, bool X3, bool BF16>
-__device__ __forceinline__ void encode_store2(unsigned char* base, int lo_delta, int row, const float (&x)[2][3]) {
+__device__ __forceinline__ void encode_store(unsigned char* base, int lo_delta, int row, const float (&x)[ENC_ROWS][3]) {
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < ENC_ROWS; ++r)
 #pragma unroll
-    for (int d = 0; d < 3; ++d) put16<X3, BF16>(base, lo_delta, row + 64 * r, d, x[r][d]);
+    for (int d = 0; d < 3; ++d) put16<X3, BF16>(base, lo_delta, row + 32 * r, d, x[r][d]);
 #pragma unroll 1
   for (int f = 0; f < L; ++f) {
     const float sc = (float)(1 << f);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      const float v0 = x[0][d] * sc, v1 = x[1][d] * sc;  // exact (power of two)
-      const float s0 = sinf(v0), s1 = sinf(v1);
-      const float c0 = sinf(__fadd_rn(v0, AON_HALF_PI_F)), c1 = sinf(__fadd_rn(v1, AON_HALF_PI_F));
-      put16<X3, BF16>(base, lo_delta, row, 3 + 3 * f + d, s0);
-      put16<X3, BF16>(base, lo_delta, row + 64, 3 + 3 * f + d, s1);
-      put16<X3, BF16>(base, lo_delta, row, 3 + 3 * L + 3 * f + d, c0);
-      put16<X3, BF16>(base, lo_delta, row + 64, 3 + 3 * L + 3 * f + d, c1);
+      float sn[ENC_ROWS], cs[ENC_ROWS];
+#pragma unroll
+      for (int r = 0; r < ENC_ROWS; ++r) {
+        const float v = x[r][d] * sc;  // exact (power of two)
+        sn[r] = sinf(v);
+        cs[r] = sinf(__fadd_rn(v, AON_HALF_PI_F));
+      }
+#pragma unroll
+      for (int r = 0; r < ENC_ROWS; ++r) {
+        put16<X3, BF16>(base, lo_delta, row + 32 * r, 3 + 3 * f + d, sn[r]);
+        put16<X3, BF16>(base, lo_delta, row + 32 * r, 3 + 3 * L + 3 * f + d, cs[r]);
+      }
     }
   }
 #pragma unroll
-  for (int k = 3 + 6 * L; k < NK; ++k) {
-    put16<X3, BF16>(base, lo_delta, row, k, 0.f);
-    put16<X3, BF16>(base, lo_delta, row + 64, k, 0.f);
-  }
+  for (int k = 3 + 6 * L; k < NK; ++k)
+#pragma unroll
+    for (int r = 0; r < ENC_ROWS; ++r) put16<X3, BF16>(base, lo_delta, row + 32 * r, k, 0.f);
 }
 
 template <bool X3, bool BF16>
@@ -479,14 +491,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     // leader's FULL: its own producer's arrive.expect_tx + the peer relay's "my half landed" arrive
     for (int i = 0; i < NSTAGE; ++i) { ptx::mbar_init(bar(BAR_FULL + i), rank == 0 ? 2 : 1); ptx::mbar_init(bar(BAR_EMPTY + i), 1); }
     // DEMPTY / CHUNK live in the leader and count the publishing warps of BOTH CTAs: 8 epilogue warps drain an
-    // accumulator, one warp per lane quadrant (4) publishes a hidden chunk, the 2 encoder warps an aux chunk
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(BAR_DFULL + i), 1); ptx::mbar_init(bar(BAR_DEMPTY + i), 16); }
-    for (int i = 0; i < NUM_CHUNK_IDS; ++i) ptx::mbar_init(bar(BAR_CHUNK + i), i < 8 ? 8 : 4);
-    ptx::mbar_init(bar(BAR_EFREE), 1);
+    // accumulator, one warp per lane quadrant (4) publishes a hidden chunk, the 4 encoder warps an aux chunk
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar(BAR_DFULL + i), 2); ptx::mbar_init(bar(BAR_DEMPTY + i), 16); }
+    for (int i = 0; i < NUM_CHUNK_IDS; ++i) ptx::mbar_init(bar(BAR_CHUNK + i), 8);
+    ptx::mbar_init(bar(BAR_EFREE), 2);   // both MMA issuers commit it
     ptx::mbar_init(bar(BAR_XW), 4);
     ptx::fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 8) {
     ptx::tmem_alloc2(sm_u32 + SP::BARS + 8 * BAR_TMEM, 512);
     ptx::tmem_relinquish2();
   }
@@ -514,6 +526,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   ptx::cluster_sync_all();   // barrier inits + TMEM allocation of both CTAs visible before any remote arrive / MMA
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  if (warp < 8) {   // both accumulators start zeroed (every MMA accumulates)
+    const uint32_t zb = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 256u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ptx::tmem_st32_zero(zb + i * 32u);
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
   // the leader's CHUNK / DEMPTY / FULL barriers as shared::cluster addresses (valid from either CTA)
   const uint32_t lead_bars = ptx::mapa(bars, 0);
   auto lbar = [&](int slot) { return lead_bars + 8u * slot; };
@@ -522,7 +543,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     if (p.tl != nullptr && blockIdx.x == 0 && s < 4) p.tl[((role * 4 + s) * MAX_UNITS + ui) * 4 + ev] = clock64() - t_start;
   };
 
-  if (warp == 0) {
+  if (warp >= 12) {
+    ptx::setmaxnreg_dec<REGS_CONTROL>();
+  if (warp == 12) {
     // ================================ weight producer ================================
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
@@ -548,7 +571,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 14) {
     if (lane == 0 && rank == 1) {
       // ================================ peer relay ================================
       // mbarrier.try_wait is CTA-local, so the leader cannot watch this CTA's FULL barriers: forward each
@@ -566,14 +589,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           }
         }
       }
-    } else if (lane == 0) {
-      // ================================ MMA issuer (leader CTA) ================================
+    }
+  }
+  if ((warp == 13 || warp == 14) && lane == 0 && rank == 0) {
+      // ================================ MMA issuers A (warp 14) and B (warp 13), leader CTA ================================
+      // Issuing one weight stage (barrier test + fence + 2-3 tcgen05.mma + commit) costs one thread ~400 cycles of
+      // serial latency (measured) -- as long as the MMAs of the stage take to execute -- so a single issuer cannot
+      // keep the tensor pipe fed.  Two threads in different warps take alternate stages (global stage number
+      // parity).  All MMAs of a unit accumulate into the same TMEM tile, which commutes; nothing overwrites (the
+      // epilogue zeroes the accumulator as it drains it).  tcgen05.commit tracks the committing thread's own MMAs, so
+      // both commit the accumulator-full (and encoding-free) barriers, which count 2.
+      const uint32_t me = warp == 14 ? 0u : 1u;
       constexpr uint32_t IDESC128 = ptx::idesc_f16(256, 128, BF16 ? 1 : 0);   // M = 256 over the pair
       constexpr uint32_t IDESC256 = ptx::idesc_f16(256, 256, BF16 ? 1 : 0);
       constexpr uint32_t A_LBO = (2048u >> 4) << 16;  // A operand: 128 rows x 16 B per k-group
       const uint32_t base16 = sm_u32 >> 4;
       const uint32_t ring16 = (sm_u32 + SP::RING) >> 4;
-      uint32_t slot = 0, phase = 0, g = 0;
+      uint32_t slot = 0, phase = 0, g = 0, n = 0;   // slot / phase / number of the NEXT stage of the common sequence
+      auto advance = [&](uint32_t k) {
+        n += k; slot += k;
+        if (slot >= (uint32_t)NSTAGE) { slot -= NSTAGE; phase ^= 1; }
+      };
+      auto chunk_parity = [&](uint32_t w, int smp) { return (((uint32_t)smp & (w >> 21)) ^ (w >> 22)) & 1u; };
       for (int s = 0; s < S; ++s) {
         for (int ui = 0; ui < P.n_units; ++ui, ++g) {
           const Unit& u = P.u[ui];
@@ -583,65 +620,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           const uint32_t b_lbo = (n128 * 64u) << 16;            // (N/2 rows * 16 B) >> 4 in the LBO field
           const uint32_t b_kstep16 = n128 * 128u;               // one K=16 step of B: N/2 * 32 B, >> 4
           const int n_chunks = u.n_chunks;
-          wait_bar(bar(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1, p.err_flag, 2);
-          ptx::tc_fence_after();
-          mark(0, s, ui, 0);
           const uint32_t d_tmem = tmem_base + b * 256u;
-          {  // chunk 0 = bias rows x ones columns: initialises the accumulator (one MMA in every mode)
+          // Every MMA of a unit accumulates (the epilogue leaves the accumulator zeroed), so the two issuers need no
+          // ordering between their MMAs; both wait for the accumulator to be drained before their first one.
+          bool unit_wait = true;
+          if ((n & 1u) == me) {
+            // chunk 0 = bias rows x ones columns (one MMA in every mode)
+            wait_bar(bar(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1, p.err_flag, 2);
+            unit_wait = false;
             wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
             ptx::tc_fence_after();
+            if (me == 0) mark(0, s, ui, 0);
             const uint32_t bd = (ring16 + slot * (SP::STAGE >> 4)) | b_lbo;
-            ptx::mma2_f16_ss(d_tmem, mk_desc((base16 + (u.ch[0] & 0xFFFFu)) | A_LBO), mk_desc(bd), idesc, 0);
+            ptx::mma2_f16_ss(d_tmem, mk_desc((base16 + (u.ch[0] & 0xFFFFu)) | A_LBO), mk_desc(bd), idesc, 1);
             ptx::mma_commit2(bar(BAR_EMPTY + slot), 3);
-            if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
           }
+          advance(1);
+          bool hidden_ready = false;
+          uint32_t w = u.ch[1];
           for (int c = 1; c < n_chunks; ++c) {
-            const uint32_t w = u.ch[c];
-            if (w & (1u << 20)) {
-              const uint32_t parity = (((uint32_t)s & (w >> 21)) ^ (w >> 22)) & 1u;
-              wait_bar(bar(BAR_CHUNK + ((w >> 16) & 15)), parity, p.err_flag, 3);
-              ptx::tc_fence_after();
-            }
-            if (c == 1) mark(0, s, ui, 1);
-            if (c == n_chunks - 1) mark(0, s, ui, 2);
-            const uint32_t a_hi = (base16 + (w & 0xFFFFu)) | A_LBO;
-            const uint32_t ksteps = (w >> 23) & 3;
-            if (X3) {
-              const uint32_t a_lo = a_hi + (((w >> 25) & 31u) << 8);  // (lo offset >> 12) << 12 >> 4
-              for (uint32_t ks = 0; ks < ksteps; ++ks) {
-                wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
-                ptx::tc_fence_after();
-                const uint32_t bd = (ring16 + slot * (SP::STAGE >> 4)) | b_lbo;   // hi rows; lo rows follow at +N/2*32 B
-                ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + ks * 256u), mk_desc(bd), idesc, 1);
-                ptx::mma2_f16_ss(d_tmem, mk_desc(a_lo + ks * 256u), mk_desc(bd), idesc, 1);
-                ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + ks * 256u), mk_desc(bd + b_kstep16), idesc, 1);
-                ptx::mma_commit2(bar(BAR_EMPTY + slot), 3);
-                if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+            const uint32_t wn = u.ch[c + 1 < n_chunks ? c + 1 : c];
+            const uint32_t nst = X3 ? ((w >> 23) & 3u) : 1u;
+            const uint32_t ks = (me ^ n) & 1u;          // which of the chunk's stages is mine (if it has two)
+            if (nst == 2u || ks == 0u) {
+              uint32_t my_slot = slot + ks, my_phase = phase;
+              if (my_slot >= (uint32_t)NSTAGE) { my_slot -= NSTAGE; my_phase ^= 1; }
+              const uint32_t id = (w >> 16) & 15u;
+              if (unit_wait) { wait_bar(bar(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1, p.err_flag, 2); unit_wait = false; }
+              if ((w & (1u << 20)) && !(hidden_ready && id < 8u)) {
+                wait_bar(bar(BAR_CHUNK + id), chunk_parity(w, s), p.err_flag, 3);
+                if (id < 8u) {
+                  // all hidden inputs of this unit already published?  (each epilogue warp publishes its chunks in
+                  // order, so the last even + last odd chunk imply the rest; hidden chunk j = chunk list entry 1 + j)
+                  const uint32_t nh = u.n_hidden, wa = u.ch[nh], wb = u.ch[nh - 1];
+                  hidden_ready = ptx::mbar_test_wait(bar(BAR_CHUNK + nh - 1), chunk_parity(wa, s)) &&
+                                 ptx::mbar_test_wait(bar(BAR_CHUNK + nh - 2), chunk_parity(wb, s));
+                }
               }
-            } else {
-              wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
+              wait_bar(bar(BAR_FULL + my_slot), my_phase, p.err_flag, 4);
               ptx::tc_fence_after();
-              const uint32_t bd = (ring16 + slot * (SP::STAGE >> 4)) | b_lbo;
-              ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd), idesc, 1);
-              ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + 256u), mk_desc(bd + b_kstep16), idesc, 1);
-              ptx::mma_commit2(bar(BAR_EMPTY + slot), 3);
-              if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+              const uint32_t bd = (ring16 + my_slot * (SP::STAGE >> 4)) | b_lbo;
+              const uint32_t a_hi = ((base16 + (w & 0xFFFFu)) | A_LBO) + (X3 ? ks * 256u : 0u);
+              if (X3) {   // hi rows; lo rows follow at +N/2*32 B
+                const uint32_t a_lo = a_hi + (((w >> 25) & 31u) << 8);  // (lo offset >> 12) << 12 >> 4
+                ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd), idesc, 1);
+                ptx::mma2_f16_ss(d_tmem, mk_desc(a_lo), mk_desc(bd), idesc, 1);
+                ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd + b_kstep16), idesc, 1);
+              } else {
+                ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd), idesc, 1);
+                ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + 256u), mk_desc(bd + b_kstep16), idesc, 1);
+              }
+              ptx::mma_commit2(bar(BAR_EMPTY + my_slot), 3);
             }
+            advance(nst);
+            w = wn;
           }
           ptx::mma_commit2(bar(BAR_DFULL + b), 3);
           if (u.last_e_use) ptx::mma_commit2(bar(BAR_EFREE), 3);
-          mark(0, s, ui, 3);
+          if (me == 0) mark(0, s, ui, 3);
         }
       }
-    }
-  } else if (warp < 4) {
+  }
+  } else if (warp >= 8) {
+    ptx::setmaxnreg_dec<REGS_ENCODER>();
     // ================================ encoder: sample positions -> operand chunks ================================
-    const int row = tid - 64;   // rows row and row + 64
-    float o[2][3], d[2][3];
-    const float* tv[2];
+    const int row = tid - 256;   // one row per encoder thread (ENC_ROWS == 1; rows row + 32 r otherwise)
+    float o[ENC_ROWS][3], d[ENC_ROWS][3];
+    const float* tv[ENC_ROWS];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const long ray = (long)blockIdx.x * 128 + row + 64 * r;
+    for (int r = 0; r < ENC_ROWS; ++r) {
+      const long ray = (long)blockIdx.x * 128 + row + 32 * r;
       const long rl = ray < p.R ? ray : (long)p.R - 1;
 #pragma unroll
       for (int k = 0; k < 3; ++k) { o[r][k] = p.rays_o[3 * rl + k]; d[r][k] = p.rays_d[3 * rl + k]; }
@@ -653,39 +701,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
       if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_CHUNK + id));
     };
     {  // view-direction encoding, once per tile (model.py:174: pos_enc(viewdirs, 0, 4))
-      float v[2][3];
+      float v[ENC_ROWS][3];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const long ray = (long)blockIdx.x * 128 + row + 64 * r;
+      for (int r = 0; r < ENC_ROWS; ++r) {
+        const long ray = (long)blockIdx.x * 128 + row + 32 * r;
         const long rl = ray < p.R ? ray : (long)p.R - 1;
 #pragma unroll
         for (int k = 0; k < 3; ++k) v[r][k] = p.viewdirs[3 * rl + k];
       }
-      encode_store2<4, 32, X3, BF16>(sm + V_OFF, LO_V, row, v);
+      encode_store<4, 32, X3, BF16>(sm + V_OFF, LO_V, row, v);
       publish(CH_V);
     }
-    float t[2] = {tv[0][0], tv[1][0]};
+    float t[ENC_ROWS];
+#pragma unroll
+    for (int r = 0; r < ENC_ROWS; ++r) t[r] = tv[r][0];
     for (int s = 0; s < S; ++s) {
-      float t_next[2];
+      float t_next[ENC_ROWS];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) t_next[r] = (s + 1 < S) ? tv[r][s + 1] : 0.f;
+      for (int r = 0; r < ENC_ROWS; ++r) t_next[r] = (s + 1 < S) ? tv[r][s + 1] : 0.f;
       // cast_rays (helper.py:25-26)
-      float x[2][3];
+      float x[ENC_ROWS][3];
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+      for (int r = 0; r < ENC_ROWS; ++r)
 #pragma unroll
         for (int k = 0; k < 3; ++k) x[r][k] = __fadd_rn(o[r][k], __fmul_rn(t[r], d[r][k]));
       if (s > 0) wait_bar(bar(BAR_EFREE), (uint32_t)((s - 1) & 1), p.err_flag, 7);
-      if (tid == 64) mark(2, s, 0, 0);
+      if (tid == 256) mark(2, s, 0, 0);
       if (KIND == AON_KIND_AUTODECODER) {
         // raw position -> operand chunk P (deformation MLP input; model_autodecoder.py:196-198)
         constexpr int PK = X3 ? 16 : 32;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < ENC_ROWS; ++r) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k) put16<X3, BF16>(sm + P_OFF, LO_P, row + 64 * r, k, x[r][k]);
+          for (int k = 0; k < 3; ++k) put16<X3, BF16>(sm + P_OFF, LO_P, row + 32 * r, k, x[r][k]);
 #pragma unroll
-          for (int k = 3; k < PK; ++k) put16<X3, BF16>(sm + P_OFF, LO_P, row + 64 * r, k, 0.f);
+          for (int k = 3; k < PK; ++k) put16<X3, BF16>(sm + P_OFF, LO_P, row + 32 * r, k, 0.f);
         }
         publish(CH_P);
         // warped position x' = x + deformation(x), handed over by the epilogue warps as fp32 in the
@@ -693,20 +743,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
         wait_bar(bar(BAR_XW), (uint32_t)(s & 1), p.err_flag, 8);
         const float* xw = reinterpret_cast<const float*>(sm + P_OFF);
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int r = 0; r < ENC_ROWS; ++r)
 #pragma unroll
-          for (int k = 0; k < 3; ++k) x[r][k] = xw[128 * k + row + 64 * r];
+          for (int k = 0; k < 3; ++k) x[r][k] = xw[128 * k + row + 32 * r];
       }
-      encode_store2<10, 64, X3, BF16>(sm + E_OFF, LO_E, row, x);
+      encode_store<10, 64, X3, BF16>(sm + E_OFF, LO_E, row, x);
       publish(CH_E0);
       publish(CH_E0 + 1);
-      if (tid == 64) mark(2, s, 0, 1);
-      t[0] = t_next[0]; t[1] = t_next[1];
+      if (tid == 256) mark(2, s, 0, 1);
+#pragma unroll
+      for (int r = 0; r < ENC_ROWS; ++r) t[r] = t_next[r];
     }
   } else {
+    ptx::setmaxnreg_inc<REGS_EPILOGUE>();
     // ================================ epilogue / per-ray state ================================
     const int quad = warp & 3;              // TMEM lane quadrant of this warp
-    const int half = (warp - 4) >> 2;       // 0: even chunks + owner of the per-ray state; 1: odd chunks
+    const int half = warp >> 2;             // 0: even chunks + owner of the per-ray state; 1: odd chunks
     const int row = quad * 32 + lane;       // ray within the tile == TMEM lane
     const bool owner = half == 0;
     const long ray = (long)blockIdx.x * 128 + row;
@@ -741,7 +793,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
         unsigned char* out_base = sm + OFF_A + row * 16;
         wait_bar(bar(BAR_DFULL + b), (g >> 1) & 1, p.err_flag, 5);
         ptx::tc_fence_after();
-        if (tid == 128) mark(1, s, ui, 0);
+        if (tid == 0) mark(1, s, ui, 0);
         const uint32_t d_addr = lane_base + b * 256u + (uint32_t)half * 32u;
 
         uint32_t r[2][32];
@@ -762,8 +814,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[1][i]) * (1.0f / SCALE_W);
           }
+          // leave the columns just read zeroed: the next unit that uses this accumulator only accumulates
+          ptx::tmem_st32_zero(d_addr + (uint32_t)j * 64u);
           if (j == n_mine - 1) {
-            // accumulator drained (my part): hand the TMEM buffer back to the MMA issuer
+            // accumulator drained and cleared (my part): hand the TMEM buffer back to the MMA issuers
+            ptx::tmem_st_wait();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_DEMPTY + b));
@@ -806,10 +861,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_CHUNK + cc));
-            if (tid == 128 && j == 0) mark(1, s, ui, 1);
+            if (tid == 0 && j == 0) mark(1, s, ui, 1);
           }
         }
-        if (tid == 128) mark(1, s, ui, 2);
+        if (tid == 0) mark(1, s, ui, 2);
 
         // head partial sums of the odd warp -> even warp (owner of the per-ray state)
         if (epi != EPI_STORE) {
@@ -881,7 +936,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   // ---- teardown ----
   ptx::tc_fence_before();
   ptx::cluster_sync_all();   // no CTA of the pair may exit (or free TMEM) while its partner can still touch it
-  if (warp == 2) {
+  if (warp == 8) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc2(tmem_base, 512);
   }

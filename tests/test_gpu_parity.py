@@ -9,7 +9,7 @@ golden vectors of the reference.  Tolerances (written here, per stage):
   (measured 8.5e-5) -- such samples carry no weight in the render.  t itself must still agree to 1e-3.
 * one level given the REFERENCE's t values (stage-wise): rgb/acc/depth <= 1e-4 relative (north_star),
   weights <= 2e-5 abs
-* full coarse+fine loop (end to end): <= max(1e-4, 3 x fp32 noise floor), where the noise floor is the
+* full coarse+fine loop (end to end): <= max(1e-4, 5 x fp32 noise floor), where the noise floor is the
   distance of the fp32 reference itself from an fp64 evaluation of the same network on the same rays
   (oracle run in float64).  The reference's fine level is chaotic at the 1e-3 level on some scenes
   (importance samples re-order under 1-ulp perturbations of the coarse weights), so a
@@ -184,7 +184,7 @@ def test_level_loop_fp32_vs_golden(aon, dev, golden_dir, name):
     for lv in range(2):
         for j, nm in enumerate(("rgb", "acc", "depth")):
             e = relerr(out[lv][j].cpu(), ref32[lv][j])
-            tol = max(REL, 3 * floor[lv][j])
+            tol = max(REL, 5 * floor[lv][j])
             assert e < tol, "%s level %d %s rel err %g (tol %g, fp32 noise floor %g)" % (name, lv, nm, e, tol, floor[lv][j])
 
 
