@@ -47,7 +47,7 @@ constexpr int MAX_CHUNKS = 11;
 constexpr int CH_E0 = 8, CH_V = 10, CH_P = 11, CH_ONE = 12, NUM_CHUNK_IDS = 13;
 enum Epi : int { EPI_STORE = 0, EPI_STORE_SIGMA = 1, EPI_RGB = 2, EPI_DEFORM = 3 };
 
-// shared-memory offsets of the operand regions (bytes from the 1024-aligned base); host and device
+// shared-memory offsets of the operand regions (bytes from the 128-byte aligned base); host and device
 constexpr int OFF_A = 0;
 __host__ __device__ constexpr int off_E(bool x3) { return x3 ? 131072 : 65536; }
 __host__ __device__ constexpr int off_V(bool x3) { return off_E(x3) + (x3 ? 32768 : 16384); }
@@ -63,13 +63,15 @@ constexpr int LO_A = 65536, LO_E = 16384, LO_V = 8192, LO_P = 4096;  // hi -> lo
 constexpr float SCALE_W = 64.0f, SCALE_A = 8.0f;
 
 // chunk word: [0,16) operand offset >> 4 | [16,20) chunk id | 20 fresh (first use of a generation: wait)
-//             | 21 writes-per-sample odd | 22 generation parity within a sample | [23,25) K steps of 16
-//             | [25,30) (lo part offset) >> 12
+//             | 21 writes-per-sample odd | 22 generation parity within a sample | [23,26) K steps of 16 (1, 2, 4)
+//             | [26,31) (lo part offset) >> 12 | 31 pair: covers chunk ids id and id + 1 (one-pass modes merge
+//             adjacent 32-wide chunks into one K=64 weight stage = 4 MMAs per issue step)
 struct Unit {
   uint8_t gemm, n_chunks, epi, relu;
   uint8_t n128;        // N / 128 (1 or 2)
   uint8_t last_e_use;  // the encoding operand may be overwritten once this unit's MMAs have completed
-  uint8_t n_hidden;    // number of 32-wide hidden input chunks (K1 / 32): chunk list entries 1 .. n_hidden
+  uint8_t n_hidden;    // number of 32-wide hidden input chunks (K1 / 32)
+  uint8_t last_hidden; // chunk list entry that holds the last hidden input chunk (0 if none)
   int16_t fold;        // >= 0: the bias stage comes from the per-call folded buffer, at fold * 16 bytes (per-rank part)
   uint32_t ch[MAX_CHUNKS];
 };
@@ -82,15 +84,19 @@ struct Program {
 };
 
 // Per-CTA weight stages (each CTA of the pair streams its own N/2 rows of B):
-//   one pass : one stage per 32-wide K chunk   [4 k-groups][N/2][8] 16-bit              = N/2 * 64 bytes
+//   one pass : one stage per chunk entry (K = 64 for merged pairs, 32 otherwise) [K/8 k-groups][N/2][8] = N/2 * 2K bytes
 //   x3       : one stage per K=16 step         hi [2 k-groups][N/2][8], then lo likewise = N/2 * 64 bytes
 //   bias     : one stage per unit (chunk CH_ONE, K=16) [2 k-groups][N/2][8]              = N/2 * 32 bytes
 __host__ __device__ inline int chunk_id(uint32_t w) { return (int)((w >> 16) & 15u); }
-__host__ __device__ inline int stage_bytes(const Unit& u, uint32_t w) { return (u.n128 * 4096) >> (chunk_id(w) == CH_ONE ? 1 : 0); }
-__host__ __device__ inline int chunk_stages(uint32_t w, int x3) { return (x3 && chunk_id(w) != CH_ONE) ? (int)((w >> 23) & 3) : 1; }
+__host__ __device__ inline int chunk_ksteps(uint32_t w) { return (int)((w >> 23) & 7u); }
+__host__ __device__ inline int stage_bytes(const Unit& u, uint32_t w, int x3) {
+  if (x3) return (u.n128 * 4096) >> (chunk_id(w) == CH_ONE ? 1 : 0);
+  return u.n128 * 2048 * chunk_ksteps(w);
+}
+__host__ __device__ inline int chunk_stages(uint32_t w, int x3) { return (x3 && chunk_id(w) != CH_ONE) ? chunk_ksteps(w) : 1; }
 __host__ __device__ inline long unit_bytes(const Unit& u, int x3) {
   long b = 0;
-  for (int c = 0; c < u.n_chunks; ++c) b += (long)chunk_stages(u.ch[c], x3) * stage_bytes(u, u.ch[c]);
+  for (int c = 0; c < u.n_chunks; ++c) b += (long)chunk_stages(u.ch[c], x3) * stage_bytes(u, u.ch[c], x3);
   return b;
 }
 
@@ -106,7 +112,7 @@ static Program build_program(int kind, int precision) {
   if (kind == AON_KIND_VANILLA) count[CH_E0] = count[CH_E0 + 1] = 1;
   else count[CH_P] = 1;
   count[CH_V] = 1;
-  struct Use { int ui, c, id, gen; };
+  struct Use { int ui, c, id, gen, pair; };
   Use uses[MAX_UNITS * MAX_CHUNKS];
   int n_uses = 0, last_e = -1;
   long fold_off = 0;
@@ -128,14 +134,20 @@ static Program build_program(int kind, int precision) {
       u.fold = (int16_t)(fold_off / 16);
       fold_off += g[gi].N / 2 * 32;
     }
-    int ids[MAX_CHUNKS], nc = 0;
+    int ids[MAX_CHUNKS], pairs[MAX_CHUNKS] = {0}, nc = 0;
     ids[nc++] = CH_ONE;          // bias first: needs no activation, so the unit can start at once
-    for (int j = 0; j < g[gi].K1 / 32; ++j) ids[nc++] = j;
-    if (g[gi].aux == AUX_E) { ids[nc++] = CH_E0; ids[nc++] = CH_E0 + 1; last_e = gi; }
+    const int step = x3 ? 1 : 2; // one-pass modes: adjacent chunks (2j, 2j+1) share one K=64 weight stage
+    for (int j = 0; j < g[gi].K1 / 32; j += step) { pairs[nc] = step == 2; ids[nc++] = j; }
+    u.last_hidden = (uint8_t)(g[gi].K1 ? nc - 1 : 0);
+    if (g[gi].aux == AUX_E) {
+      pairs[nc] = step == 2; ids[nc++] = CH_E0;
+      if (step == 1) ids[nc++] = CH_E0 + 1;
+      last_e = gi;
+    }
     if (g[gi].aux == AUX_V) ids[nc++] = CH_V;
     if (g[gi].aux == AUX_P) ids[nc++] = CH_P;
     u.n_chunks = nc;
-    for (int c = 0; c < nc; ++c) uses[n_uses++] = {gi, c, ids[c], count[ids[c]] - 1};
+    for (int c = 0; c < nc; ++c) uses[n_uses++] = {gi, c, ids[c], count[ids[c]] - 1, pairs[c]};
     if (epi <= EPI_STORE_SIGMA)
       for (int j = 0; j < u.n128 * 4; ++j) count[j]++;
     if (epi == EPI_DEFORM) { count[CH_E0]++; count[CH_E0 + 1]++; }
@@ -150,12 +162,12 @@ static Program build_program(int kind, int precision) {
     else if (x.id == CH_V) { off = off_V(x3); lo = LO_V; }
     else if (x.id == CH_P) { off = off_P(x3); lo = LO_P; }
     else { off = off_ONE(x3); lo = 0; }
-    const int ksteps = (x.id == CH_ONE || (x3 && x.id == CH_P)) ? 1 : 2;
+    const int ksteps = (x.id == CH_ONE || (x3 && x.id == CH_P)) ? 1 : (x.pair ? 4 : 2);
     const int fresh = x.id != CH_ONE && (x.gen != seen_gen[x.id] || x.id == CH_V);
     seen_gen[x.id] = x.gen;
     uint32_t w = (uint32_t)(off >> 4) | ((uint32_t)x.id << 16) | ((uint32_t)fresh << 20) |
                  ((uint32_t)(count[x.id] & 1) << 21) | ((uint32_t)(x.gen & 1) << 22) | ((uint32_t)ksteps << 23) |
-                 ((uint32_t)(lo >> 12) << 25);
+                 ((uint32_t)(lo >> 12) << 26) | ((uint32_t)x.pair << 31);
     P.u[x.ui].ch[x.c] = w;
   }
   long bytes = 0;
@@ -230,7 +242,7 @@ __global__ void pack_stream_kernel(Program P, PackSrc src, uint16_t* __restrict_
     long rel = hidx - src.unit_byte0[ui] / 2;   // element within the unit
     int c = 0, stage = 0;
     for (;; ++c) {
-      const long se = stage_bytes(u, u.ch[c]) / 2;
+      const long se = stage_bytes(u, u.ch[c], X3) / 2;
       const long ce = (long)chunk_stages(u.ch[c], X3) * se;
       if (rel < ce) { stage = (int)(rel / se); rel -= (long)stage * se; break; }
       rel -= ce;
@@ -321,10 +333,12 @@ struct SmemPlan {
   static constexpr int BARS = XCH + 2048;
   static constexpr int BAR_BYTES = 384;
   static constexpr int RING = (BARS + BAR_BYTES + 127) / 128 * 128;
-  static constexpr int STAGE = 8192;                   // ring slot size (stages of 128-wide layers / bias stages use less)
-  static constexpr int NSTAGE_RAW = (SMEM_MAX - 1024 - RING) / STAGE;
-  static constexpr int NSTAGE = NSTAGE_RAW > MAX_STAGES ? MAX_STAGES : NSTAGE_RAW;
-  static constexpr int TOTAL = RING + NSTAGE * STAGE + 1024;
+  static constexpr int STAGE = X3 ? 8192 : 16384;      // ring slot size (stages of 128-wide layers / bias stages use less)
+  static constexpr int NSTAGE_RAW = (SMEM_MAX - 128 - RING) / STAGE;   // 128 B of slack for aligning the dynamic smem base
+  // even: the two MMA issuers take alternate stages, so with an even ring each thread only ever re-uses slots whose
+  // previous round it waited for itself (a parity wait on a barrier that is still a round behind passes falsely)
+  static constexpr int NSTAGE = (NSTAGE_RAW > MAX_STAGES ? MAX_STAGES : NSTAGE_RAW) & ~1;
+  static constexpr int TOTAL = RING + NSTAGE * STAGE + 128;
   static_assert(NSTAGE >= 3, "weight ring too small");
 };
 
@@ -470,8 +484,9 @@ __device__ __forceinline__ void pair_bar_arrive(int id) { asm volatile("bar.arri
 template <int KIND, bool X3, bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_constant__ TcParams p) {
   using SP = SmemPlan<KIND, X3>;
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  // no-swizzle operand layouts and bulk copies need 16-byte / 128-byte alignment only
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* sm = smem_raw + ((128u - (ptx::smem_u32(smem_raw) & 127u)) & 127u);
   const uint32_t sm_u32 = ptx::smem_u32(sm);
   float* s_par = reinterpret_cast<float*>(sm + SP::PARAMS);
   float* s_xch = reinterpret_cast<float*>(sm + SP::XCH);
@@ -556,7 +571,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           const Unit& u = P.u[ui];
           for (int c = 0; c < u.n_chunks; ++c) {
             const uint32_t w = u.ch[c];
-            const uint32_t bytes = (uint32_t)stage_bytes(u, w);
+            const uint32_t bytes = (uint32_t)stage_bytes(u, w, X3);
             const int nst = chunk_stages(w, X3);
             for (int i = 0; i < nst; ++i) {
               const char* from = src;
@@ -640,7 +655,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           uint32_t w = u.ch[1];
           for (int c = 1; c < n_chunks; ++c) {
             const uint32_t wn = u.ch[c + 1 < n_chunks ? c + 1 : c];
-            const uint32_t nst = X3 ? ((w >> 23) & 3u) : 1u;
+            const uint32_t nst = X3 ? ((w >> 23) & 7u) : 1u;
             const uint32_t ks = (me ^ n) & 1u;          // which of the chunk's stages is mine (if it has two)
             if (nst == 2u || ks == 0u) {
               uint32_t my_slot = slot + ks, my_phase = phase;
@@ -649,12 +664,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
               if (unit_wait) { wait_bar(bar(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1, p.err_flag, 2); unit_wait = false; }
               if ((w & (1u << 20)) && !(hidden_ready && id < 8u)) {
                 wait_bar(bar(BAR_CHUNK + id), chunk_parity(w, s), p.err_flag, 3);
+                if (w >> 31) wait_bar(bar(BAR_CHUNK + id + 1), chunk_parity(w, s), p.err_flag, 3);   // merged pair
                 if (id < 8u) {
                   // all hidden inputs of this unit already published?  (each epilogue warp publishes its chunks in
-                  // order, so the last even + last odd chunk imply the rest; hidden chunk j = chunk list entry 1 + j)
-                  const uint32_t nh = u.n_hidden, wa = u.ch[nh], wb = u.ch[nh - 1];
-                  hidden_ready = ptx::mbar_test_wait(bar(BAR_CHUNK + nh - 1), chunk_parity(wa, s)) &&
-                                 ptx::mbar_test_wait(bar(BAR_CHUNK + nh - 2), chunk_parity(wb, s));
+                  // order, so the last even + last odd chunk imply the rest; both share one write history = parity)
+                  const uint32_t nh = u.n_hidden, par = chunk_parity(u.ch[u.last_hidden], s);
+                  hidden_ready = ptx::mbar_test_wait(bar(BAR_CHUNK + nh - 1), par) && ptx::mbar_test_wait(bar(BAR_CHUNK + nh - 2), par);
                 }
               }
               wait_bar(bar(BAR_FULL + my_slot), my_phase, p.err_flag, 4);
@@ -662,13 +677,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
               const uint32_t bd = (ring16 + my_slot * (SP::STAGE >> 4)) | b_lbo;
               const uint32_t a_hi = ((base16 + (w & 0xFFFFu)) | A_LBO) + (X3 ? ks * 256u : 0u);
               if (X3) {   // hi rows; lo rows follow at +N/2*32 B
-                const uint32_t a_lo = a_hi + (((w >> 25) & 31u) << 8);  // (lo offset >> 12) << 12 >> 4
+                const uint32_t a_lo = a_hi + (((w >> 26) & 31u) << 8);  // (lo offset >> 12) << 12 >> 4
                 ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd), idesc, 1);
                 ptx::mma2_f16_ss(d_tmem, mk_desc(a_lo), mk_desc(bd), idesc, 1);
                 ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd + b_kstep16), idesc, 1);
               } else {
-                ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd), idesc, 1);
-                ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + 256u), mk_desc(bd + b_kstep16), idesc, 1);
+                const uint32_t nk = (w >> 23) & 7u;   // 2 (K = 32) or 4 (merged pair, K = 64)
+                for (uint32_t k = 0; k < nk; ++k)
+                  ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + k * 256u), mk_desc(bd + k * b_kstep16), idesc, 1);
               }
               ptx::mma_commit2(bar(BAR_EMPTY + my_slot), 3);
             }
@@ -678,6 +694,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           ptx::mma_commit2(bar(BAR_DFULL + b), 3);
           if (u.last_e_use) ptx::mma_commit2(bar(BAR_EFREE), 3);
           if (me == 0) mark(0, s, ui, 3);
+          if (u.n_hidden && !hidden_ready) {
+            // Parity waits are only sound if this thread never falls a whole generation behind a barrier it will test
+            // later: it may not have owned a stage of the last hidden chunks of this unit, so it observes their
+            // generation here (each epilogue warp publishes in order: last even + last odd chunk imply the rest).
+            const uint32_t nh = u.n_hidden, par = chunk_parity(u.ch[u.last_hidden], s);
+            wait_bar(bar(BAR_CHUNK + nh - 1), par, p.err_flag, 3);
+            wait_bar(bar(BAR_CHUNK + nh - 2), par, p.err_flag, 3);
+          }
         }
       }
   }
