@@ -247,13 +247,14 @@ sample_pdf_kernel(const float* __restrict__ t_coarse, long t_stride, const float
     const float padw = __fdiv_rn(padding, (float)nw);
     const float wsum = __fadd_rn(wsum0, padding);
     // cdf[0]=0, cdf[k]=min(1, cumsum(pdf)[k-1]) for k=1..nw-1, cdf[nw]=1   (nw+1 = nb entries)
-    // sequential fp32 cumsum like torch.cumsum; done by lane 0 (63 adds).
+    // pdf in parallel, then the sequential fp32 cumsum of torch.cumsum (CPU) by lane 0 (62 adds).
+    for (int k = lane; k < nw - 1; k += 32) sc[k + 1] = __fdiv_rn(__fadd_rn(w[1 + k], padw), wsum);
+    __syncwarp();
     if (lane == 0) {
       float c = 0.f;
       sc[0] = 0.f;
       for (int k = 0; k < nw - 1; ++k) {
-        const float pdf = __fdiv_rn(__fadd_rn(w[1 + k], padw), wsum);
-        c = __fadd_rn(c, pdf);
+        c = __fadd_rn(c, sc[k + 1]);
         sc[k + 1] = fminf(1.0f, c);
       }
       sc[nw] = 1.0f;
@@ -282,16 +283,40 @@ sample_pdf_kernel(const float* __restrict__ t_coarse, long t_stride, const float
       st[nc + j] = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
     }
     __syncwarp();
-    // rank sort of the ntot values
+    // The reference sorts cat[t_coarse, samples] (helper.py:250).  t_coarse is sorted; if the samples came out
+    // non-decreasing too (always, up to rounding, for the deterministic u table) the stable sort is a merge:
+    //   rank(coarse i) = i + #{samples < t_i},  rank(sample j) = #{coarse <= s_j} + j      (two binary searches)
+    // otherwise (unsorted random u, or a 1-ulp inversion at a bracket boundary) fall back to a rank sort.
     float* out = t_fine + ray * (long)ntot;
-    for (int i = lane; i < ntot; i += 32) {
-      const float v = st[i];
-      int rank = 0;
-      for (int j = 0; j < ntot; ++j) {
-        const float x = st[j];
-        rank += (x < v) || (x == v && j < i);
+    bool sorted = true;
+    for (int j = lane; j < nf - 1; j += 32) sorted = sorted && (st[nc + j] <= st[nc + j + 1]);
+    for (int i = lane; i < nc - 1; i += 32) sorted = sorted && (st[i] <= st[i + 1]);
+    sorted = __all_sync(0xffffffffu, sorted);
+    if (sorted) {
+      for (int i = lane; i < ntot; i += 32) {
+        const float v = st[i];
+        int lo = 0, hi, rank;
+        if (i < nc) {          // first sample index with s >= v
+          hi = nf;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (st[nc + mid] < v) lo = mid + 1; else hi = mid; }
+          rank = i + lo;
+        } else {               // first coarse index with t > v
+          hi = nc;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (st[mid] <= v) lo = mid + 1; else hi = mid; }
+          rank = (i - nc) + lo;
+        }
+        out[rank] = v;
       }
-      out[rank] = v;
+    } else {
+      for (int i = lane; i < ntot; i += 32) {
+        const float v = st[i];
+        int rank = 0;
+        for (int j = 0; j < ntot; ++j) {
+          const float x = st[j];
+          rank += (x < v) || (x == v && j < i);
+        }
+        out[rank] = v;
+      }
     }
     __syncwarp();
   }
