@@ -18,7 +18,9 @@ Differences from the reference, all result-preserving:
 """
 from __future__ import annotations
 
+import json
 import math
+import os
 from types import SimpleNamespace
 from typing import Dict, Optional
 
@@ -61,6 +63,24 @@ class LitModel(nn.Module):
         return -10.0 * torch.log(mse) / np.log(10)
 
 
+def to8b(x):
+    return (255 * np.clip(x, 0, 1)).astype(np.uint8)
+
+
+def store_image(dirpath, rgbs, name):
+    """models/utils.py:21-27: {dirpath}/{name}{NNN}.jpg"""
+    from PIL import Image
+    for i, rgb in enumerate(rgbs):
+        Image.fromarray(to8b(rgb.detach().cpu().numpy())).save(os.path.join(dirpath, "%s%s.jpg" % (name, str(i).zfill(3))))
+
+
+def write_stats(fpath, *stats):
+    """models/utils.py:62-73"""
+    d = {st["name"]: {k: float(w) for k, w in st.items() if k not in ("name", "scene_wise")} for st in stats}
+    with open(fpath, "w") as fp:
+        json.dump(d, fp, indent=4, sort_keys=True)
+
+
 class _LitCommon(LitModel):
     near, far, white_bkgd = 2.0, 6.0, True     # datasets/sapien.py:72-73 constants; setup() may override
 
@@ -99,6 +119,39 @@ class _LitCommon(LitModel):
         for pg in optimizer.param_groups:
             pg["lr"] = lr
         optimizer.step(closure=optimizer_closure)
+
+    # ---- evaluation artefacts (model.py:459-507; interface.py:64-99,125-138) ----
+    @torch.no_grad()
+    def psnr_each(self, preds, gts):
+        return torch.stack([self.psnr_legacy(p, g) for p, g in zip(preds, gts)])
+
+    @torch.no_grad()
+    def psnr(self, preds, gts, i_train=None, i_val=None, i_test=None, name="PSNR"):
+        m = self.psnr_each(preds, gts).mean().item()
+        return {"name": name, "mean": m, "test": m}
+
+    @torch.no_grad()
+    def test_epoch_end(self, outputs):
+        """outputs: list of test_step dicts, one per image ([H*W,3] rgb / target, [H*W] instance_mask).  Regroups them
+        per image (every rank renders whole images here, so the reference's per-pixel all_gather interleave,
+        interface.py:31-51, is not needed), computes PSNR and object-masked PSNR, and on the global-zero rank writes
+        ckpts/{exp_name}/{render_name}/imageNNN.jpg and ckpts/{exp_name}/results.json.  SSIM / LPIPS need piqa (absent)."""
+        W, H = self.hparams.img_wh
+        rgbs = [o["rgb"].reshape(H, W, 3) for o in outputs]
+        targets = [o["target"].reshape(H, W, 3) for o in outputs]
+        masks = [o["instance_mask"].reshape(H, W).bool() for o in outputs]
+        psnr = self.psnr(rgbs, targets)
+        obj = [(r[m], t[m]) for r, t, m in zip(rgbs, targets, masks) if m.any()]
+        psnr_obj = self.psnr([a for a, _ in obj], [b for _, b in obj], name="PSNR_obj") if obj else {"name": "PSNR_obj", "mean": float("nan"), "test": float("nan")}
+        self.log("test/psnr", psnr["test"])
+        self.log("test/psnr_obj", psnr_obj["test"])
+        if self.trainer.is_global_zero:
+            exp, ren = getattr(self.hparams, "exp_name", "exp"), getattr(self.hparams, "render_name", "render")
+            image_dir = os.path.join(getattr(self.hparams, "ckpt_root", "ckpts"), exp, ren)
+            os.makedirs(image_dir, exist_ok=True)
+            store_image(image_dir, rgbs, "image")
+            write_stats(os.path.join(os.path.dirname(image_dir), "results.json"), psnr, psnr_obj)
+        return psnr, psnr_obj
 
     @staticmethod
     def _squeeze(batch, keep=()):
@@ -249,4 +302,6 @@ class Trainer:
     def test(self, system: _LitCommon, batches) -> list:
         system.trainer = self
         system.eval()
-        return [system.test_step(b, i) for i, b in enumerate(batches)]
+        outputs = [system.test_step(b, i) for i, b in enumerate(batches)]
+        system.test_results = system.test_epoch_end(outputs) if all(o.get("target") is not None for o in outputs) else None
+        return outputs

@@ -35,3 +35,21 @@ def test_psnr_protocol_short(built_lib):
     for name, p, dlt, cross in rows[1:]:
         assert abs(dlt) < 0.1, rows                                      # north_star: PSNR within 0.1 dB of the reference
     assert rows[1][3] > 80, rows                                         # f16x3 render ~identical to the reference render
+
+
+def test_run_cli_train_then_eval(tmp_path, built_lib, monkeypatch):
+    """run.py surface: train a few steps -> last.ckpt (PL-style state_dict keys) -> --run_eval writes the reference's
+    artefacts: ckpts/{exp_name}/{render_name}/imageNNN.jpg + results.json (model.py:494-505)."""
+    import json, os
+    from aon_b200 import data, run
+    root = data.write_synthetic_scene(str(tmp_path / "scene"), (32, 24), n_train=4, n_val=1, n_test=2, seed=3)
+    monkeypatch.chdir(tmp_path)
+    common = ["--root_dir", root, "--img_wh", "32", "24", "--exp_name", "t", "--output_path", str(tmp_path / "results")]
+    run.main(run.get_opts(common + ["--run_max_steps", "20"]))
+    sd = torch.load(tmp_path / "results" / "t" / "last.ckpt")["state_dict"]
+    assert "model.coarse_mlp.pts_linears.0.weight" in sd and "model.fine_mlp.rgb_layer.bias" in sd
+    s = run.main(run.get_opts(common + ["--run_eval", "--render_name", "rr", "--precision", "f16x3"]))
+    assert sorted(os.listdir(tmp_path / "ckpts" / "t" / "rr")) == ["image000.jpg", "image001.jpg"]
+    res = json.load(open(tmp_path / "ckpts" / "t" / "results.json"))
+    assert set(res) == {"PSNR", "PSNR_obj"} and set(res["PSNR"]) == {"mean", "test"}
+    assert abs(res["PSNR"]["test"] - s.logged["test/psnr"]) < 1e-6
