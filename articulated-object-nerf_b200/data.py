@@ -164,3 +164,147 @@ def write_synthetic_scene(root: str, img_wh: Tuple[int, int] = (64, 48), n_train
         with open(os.path.join(root, split, "transforms.json"), "w") as f:
             json.dump({"focal": focal, "frames": frames}, f)
     return root
+
+
+# --------------------------------------------------------------------------------------------------------------
+# articulated multi-instance format (datasets/sapien_multi.py) + synthetic two-part "scissor" writer
+# --------------------------------------------------------------------------------------------------------------
+IDX_TO_DEG = {0: 0, 1: 10, 2: 20, 3: 30, 4: 40, 5: 50, 6: 60, 7: 70, 8: 80, 9: 90}     # sapien_multi.py:11-14 ("train")
+
+
+def create_spheric_poses(radius: float = 4.0) -> Tensor:
+    """sapien_multi.py:29-72: 40 poses on a circle, elevation -30 deg, [40,4,4]."""
+    def pose(theta, phi, r):
+        t = torch.eye(4); t[2, 3] = r
+        ph, th = math.radians(phi), math.radians(theta)
+        rp = torch.tensor([[1, 0, 0, 0], [0, math.cos(ph), -math.sin(ph), 0], [0, math.sin(ph), math.cos(ph), 0], [0, 0, 0, 1]], dtype=torch.float32)
+        rt = torch.tensor([[math.cos(th), 0, -math.sin(th), 0], [0, 1, 0, 0], [math.sin(th), 0, math.cos(th), 0], [0, 0, 0, 1]], dtype=torch.float32)
+        fix = torch.tensor([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=torch.float32)
+        return fix @ (rt @ (rp @ t))
+    return torch.stack([pose(a, -30.0, radius) for a in np.linspace(-180, 180, 41)[:-1]], 0)
+
+
+class SapienDatasetMulti:
+    """datasets/sapien_multi.py:124-479: {root}/{instance}/train/{deg}_degree/{rgb,seg}/r_i.png + transforms.json with
+    ``camera_angle_x``; train samples = 4096 random pixels of a random (instance, articulation state, image); val = one
+    full image; test = 19 frames on the spherical path (articulation_id = frame index -> interpolated code table)."""
+
+    def __init__(self, root_dir, split="train", img_wh=(320, 240), model_type=None, white_back=True, eval_inference=None,
+                 device="cuda", seed=0):
+        self.root_dir, self.split, self.img_wh, self.white_back = root_dir, split, tuple(img_wh), white_back
+        self.device = torch.device(device)
+        self.ids = sorted(f.name for f in os.scandir(root_dir) if f.is_dir())
+        self.samples_per_epoch = 4000
+        self.near, self.far = 2.0, 6.0
+        w, h = self.img_wh
+        self.image_sizes = np.array([[h, w] for _ in range(19 if eval_inference is not None else 1)])
+        self.poses_test = create_spheric_poses(4.0)
+        self.rng = np.random.RandomState(seed)
+        self.gen = torch.Generator(device=self.device).manual_seed(seed)
+        self._cache = {}
+
+    def _states(self, inst):
+        d = [f.name for f in os.scandir(os.path.join(self.root_dir, inst, "train")) if f.is_dir()]
+        return sorted(d, key=lambda s: int(s.split("_")[0]))
+
+    def _frame(self, inst, state, image_id, c2w=None):
+        key = (inst, state, image_id, c2w is None)
+        if key in self._cache:
+            return self._cache[key]
+        from PIL import Image
+        base = os.path.join(self.root_dir, inst, "train", state)
+        meta = json.load(open(os.path.join(base, "transforms.json")))
+        files = sorted(os.listdir(os.path.join(base, "rgb")), key=lambda fn: int(fn.split("_")[1].split(".")[0]))
+        fn = files[image_id % len(files)]
+        w, h = self.img_wh
+        focal = 0.5 * h / np.tan(0.5 * meta["camera_angle_x"]) * (w / 320)            # sapien_multi.py:281-283
+        if c2w is None:
+            c2w = torch.tensor(meta["frames"][fn.split(".")[0]], dtype=torch.float32)
+        img = np.asarray(Image.open(os.path.join(base, "rgb", fn)).convert("RGB").resize((w, h), Image.LANCZOS), dtype=np.float32) / 255.0
+        seg = np.asarray(Image.open(os.path.join(base, "seg", fn)).resize((w, h), Image.LANCZOS)) > 0
+        bg = 1.0 if self.white_back else 0.0
+        img = np.where(seg[..., None], img, bg).astype(np.float32)                       # get_masked_img_seg
+        o, d = L.raygen(h, w, float(focal), c2w[:3, :4], self.device)
+        out = (o, d, torch.from_numpy(img.reshape(-1, 3)).to(self.device), torch.from_numpy(seg.reshape(-1)).to(self.device))
+        if len(self._cache) < 4096:
+            self._cache[key] = out
+        return out
+
+    def __len__(self):
+        return self.samples_per_epoch if self.split == "train" else (1 if self.split == "val" else 19)
+
+    def __getitem__(self, idx) -> Dict[str, object]:
+        w, h = self.img_wh
+        inst_idx = int(self.rng.randint(0, len(self.ids)))
+        inst = self.ids[inst_idx]
+        states = self._states(inst)
+        if self.split in ("train", "val"):
+            deg_idx = int(self.rng.randint(0, len(states)))
+            o, d, rgb, seg = self._frame(inst, states[deg_idx], int(self.rng.randint(0, 59)))
+            if self.split == "train":
+                pix = torch.randint(0, h * w, (4096,), generator=self.gen, device=self.device)
+                o, d, rgb, seg = o[pix], d[pix], rgb[pix], seg[pix]
+            s = {"deg": np.float32(np.deg2rad(IDX_TO_DEG[deg_idx])), "articulation_id": torch.tensor([deg_idx], device=self.device)}
+        else:
+            o, d, rgb, seg = self._frame(inst, states[0], idx, c2w=self.poses_test[idx])
+            s = {"articulation_id": torch.tensor([idx], device=self.device)}
+        s.update(rays_o=o, rays_d=d, viewdirs=d, target=rgb, instance_mask=seg, instance_id=torch.tensor([inst_idx], device=self.device),
+                 img_wh=np.array((w, h)))
+        return s
+
+    def ray_batches(self) -> Iterator[Dict[str, object]]:
+        while True:
+            yield self[0]
+
+
+def _rot_z(deg):
+    a = math.radians(deg)
+    return np.array([[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1.0]])
+
+
+def _trace_scissor(o, d, deg):
+    """Two slabs hinged at the origin: a fixed one along +x and one rotated by `deg` about z.  RGB [N,3], mask [N]."""
+    n = d.shape[0]
+    t_best = np.full(n, np.inf); col = np.zeros((n, 3)); nrm = np.zeros((n, 3))
+    for rot, rgb in ((np.eye(3), (0.8, 0.3, 0.25)), (_rot_z(deg), (0.25, 0.4, 0.85))):
+        ol, dl = rot.T @ o, d @ rot                          # ray in the part's frame
+        c, h = np.array([0.55, 0.0, 0.0]), np.array([0.6, 0.12, 0.1])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t0, t1 = (c - h - ol) / dl, (c + h - ol) / dl
+        tn, tf = np.minimum(t0, t1), np.maximum(t0, t1)
+        tnear, tfar = tn.max(1), tf.min(1)
+        hit = (tnear < tfar) & (tnear > 0) & (tnear < t_best)
+        axis = tn.argmax(1)
+        bn = np.zeros((n, 3)); bn[np.arange(n), axis] = -np.sign(dl[np.arange(n), axis])
+        t_best = np.where(hit, tnear, t_best)
+        nrm[hit] = (bn @ rot.T)[hit]; col[hit] = rgb
+    mask = np.isfinite(t_best)
+    return col * (0.3 + 0.7 * np.clip(nrm @ _LIGHT, 0, 1))[:, None], mask
+
+
+def write_synthetic_articulated(root: str, img_wh=(64, 48), n_states: int = 4, n_images: int = 8, instances=("0001",), seed: int = 0) -> str:
+    """{root}/{inst}/train/{deg}_degree/{rgb,seg}/r_i.png + transforms.json {"camera_angle_x", "frames"}."""
+    from PIL import Image
+    w, h = img_wh
+    focal = sapien_focal(h)
+    cax = 2 * math.atan(0.5 * h * (w / 320) / focal)          # inverse of the reader's focal rule (sapien_multi.py:281-283)
+    ys, xs = np.meshgrid(np.arange(h, dtype=np.float64), np.arange(w, dtype=np.float64), indexing="ij")
+    dirs = np.stack([(xs - w / 2) / focal, -(ys - h / 2) / focal, -np.ones_like(xs)], -1).reshape(-1, 3)
+    k = seed * 7919
+    for inst in instances:
+        for si in range(n_states):
+            deg = IDX_TO_DEG[si]
+            base = os.path.join(root, inst, "train", "%d_degree" % deg)
+            os.makedirs(os.path.join(base, "rgb"), exist_ok=True); os.makedirs(os.path.join(base, "seg"), exist_ok=True)
+            frames = {}
+            for i in range(n_images):
+                c2w = sapien_camera(seed=k, radius=4.0).numpy().astype(np.float64); k += 1
+                dw = dirs @ c2w[:, :3].T
+                dw /= np.linalg.norm(dw, axis=1, keepdims=True)
+                rgb, mask = _trace_scissor(c2w[:, 3], dw, deg)
+                Image.fromarray((np.clip(rgb, 0, 1) * 255 + 0.5).astype(np.uint8).reshape(h, w, 3), "RGB").save(os.path.join(base, "rgb", "r_%d.png" % i))
+                Image.fromarray((mask.reshape(h, w) * 255).astype(np.uint8), "L").save(os.path.join(base, "seg", "r_%d.png" % i))
+                frames["r_%d" % i] = np.vstack([c2w, [0, 0, 0, 1]]).tolist()
+            with open(os.path.join(base, "transforms.json"), "w") as f:
+                json.dump({"camera_angle_x": cax, "frames": frames}, f)
+    return root

@@ -47,8 +47,10 @@ def get_opts(argv=None):
 
 
 def main(hparams):
-    if hparams.dataset_name != "sapien":
-        raise SystemExit("only the single-scene 'sapien' on-disk format is re-hosted so far (SURVEY.md 8f F2)")
+    if hparams.dataset_name not in ("sapien", "sapien_multi"):
+        raise SystemExit("dataset_name must be 'sapien' or 'sapien_multi' (datasets/__init__.py:4)")
+    multi = hparams.dataset_name == "sapien_multi"
+    Dataset = data.SapienDatasetMulti if multi else data.SapienDataset
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
     system = lit.build_system(hparams).to(dev)
@@ -60,16 +62,17 @@ def main(hparams):
     ckpt = os.path.join(result, hparams.ckpt_path or "last.ckpt")
     if hparams.run_eval:
         system.load_state_dict(torch.load(ckpt, map_location=dev)["state_dict"])
-        test = data.SapienDataset(hparams.root_dir, "test_val", tuple(hparams.img_wh), white_back=hparams.white_back,
+        test = Dataset(hparams.root_dir, "test_val", tuple(hparams.img_wh), white_back=hparams.white_back,
                                   eval_inference=hparams.render_name, device=dev)
         system.setup(datasets={"test": test})
         tr = lit.Trainer()
-        tr.test(system, ({k: (v[None] if torch.is_tensor(v) else v) for k, v in test[i].items()} for i in range(len(test))))
+        keep = ("instance_id", "articulation_id")
+        tr.test(system, ({k: (v[None] if torch.is_tensor(v) and k not in keep else v) for k, v in test[i].items()} for i in range(len(test))))
         print("test", {k: round(v, 4) for k, v in system.logged.items() if k.startswith("test/")})
         return system
-    train = data.SapienDataset(hparams.root_dir, "train", tuple(hparams.img_wh), white_back=hparams.white_back, device=dev)
+    train = Dataset(hparams.root_dir, "train", tuple(hparams.img_wh), white_back=hparams.white_back, device=dev)
     system.setup(datasets={"train": train})
-    lit.Trainer(max_steps=hparams.run_max_steps, log_every=max(1, hparams.run_max_steps // 10)).fit(system, train.ray_batches(2048))
+    lit.Trainer(max_steps=hparams.run_max_steps, log_every=max(1, hparams.run_max_steps // 10)).fit(system, train.ray_batches() if multi else train.ray_batches(2048))
     torch.save({"state_dict": system.state_dict(), "global_step": hparams.run_max_steps}, ckpt)
     return system
 
