@@ -382,6 +382,16 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int* err
   if (!ptx::mbar_try_wait(bar, parity)) wait_slow(bar, parity, err_flag, code);
 }
 
+// Lean wait for the single-thread control roles (MMA issuers, producer, relay): no time-out code.  The inlined
+// time-out path of wait_bar sits between the barrier test and the instructions that follow it, so every test cost
+// a taken branch over ~25 cold instructions and the issuers' hot loop was spread over a dozen instruction-cache
+// lines (ncu: stall_branch_resolving + stall_no_inst dominated those warps).  A hang still traps: the epilogue and
+// encoder warps keep their timed waits.
+__device__ __forceinline__ void spin_bar(uint32_t bar, uint32_t parity) {
+  while (!ptx::mbar_try_wait(bar, parity)) {
+  }
+}
+
 template <bool X3, bool BF16>
 __device__ __forceinline__ void split16(float v, uint16_t& hi, uint16_t& lo) {
   if (BF16) {
@@ -576,7 +586,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
             for (int i = 0; i < nst; ++i) {
               const char* from = src;
               if (KIND == AON_KIND_AUTODECODER && c == 0 && u.fold >= 0) from = fold_src + (size_t)u.fold * 16;
-              wait_bar(bar(BAR_EMPTY + slot), phase ^ 1, p.err_flag, 1);
+              spin_bar(bar(BAR_EMPTY + slot), phase ^ 1);
               ptx::mbar_arrive_expect_tx(bar(BAR_FULL + slot), bytes);
               ptx::bulk_g2s(sm_u32 + SP::RING + slot * SP::STAGE, from, bytes, bar(BAR_FULL + slot));
               src += bytes;
@@ -598,7 +608,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           int nst = 0;
           for (int c = 0; c < u.n_chunks; ++c) nst += chunk_stages(u.ch[c], X3);
           for (int i = 0; i < nst; ++i) {
-            wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 9);
+            spin_bar(bar(BAR_FULL + slot), phase);
             ptx::mbar_arrive_cluster(lbar(BAR_FULL + slot));
             if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
           }
@@ -641,9 +651,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           bool unit_wait = true;
           if ((n & 1u) == me) {
             // chunk 0 = bias rows x ones columns (one MMA in every mode)
-            wait_bar(bar(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1, p.err_flag, 2);
+            spin_bar(bar(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1);
             unit_wait = false;
-            wait_bar(bar(BAR_FULL + slot), phase, p.err_flag, 4);
+            spin_bar(bar(BAR_FULL + slot), phase);
             ptx::tc_fence_after();
             if (me == 0) mark(0, s, ui, 0);
             const uint32_t bd = (ring16 + slot * (SP::STAGE >> 4)) | b_lbo;
@@ -661,10 +671,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
               uint32_t my_slot = slot + ks, my_phase = phase;
               if (my_slot >= (uint32_t)NSTAGE) { my_slot -= NSTAGE; my_phase ^= 1; }
               const uint32_t id = (w >> 16) & 15u;
-              if (unit_wait) { wait_bar(bar(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1, p.err_flag, 2); unit_wait = false; }
+              if (unit_wait) { spin_bar(bar(BAR_DEMPTY + b), ((g >> 1) & 1) ^ 1); unit_wait = false; }
               if ((w & (1u << 20)) && !(hidden_ready && id < 8u)) {
-                wait_bar(bar(BAR_CHUNK + id), chunk_parity(w, s), p.err_flag, 3);
-                if (w >> 31) wait_bar(bar(BAR_CHUNK + id + 1), chunk_parity(w, s), p.err_flag, 3);   // merged pair
+                spin_bar(bar(BAR_CHUNK + id), chunk_parity(w, s));
+                if (w >> 31) spin_bar(bar(BAR_CHUNK + id + 1), chunk_parity(w, s));   // merged pair
                 if (id < 8u) {
                   // all hidden inputs of this unit already published?  (each epilogue warp publishes its chunks in
                   // order, so the last even + last odd chunk imply the rest; both share one write history = parity)
@@ -672,7 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
                   hidden_ready = ptx::mbar_test_wait(bar(BAR_CHUNK + nh - 1), par) && ptx::mbar_test_wait(bar(BAR_CHUNK + nh - 2), par);
                 }
               }
-              wait_bar(bar(BAR_FULL + my_slot), my_phase, p.err_flag, 4);
+              spin_bar(bar(BAR_FULL + my_slot), my_phase);
               ptx::tc_fence_after();
               const uint32_t bd = (ring16 + my_slot * (SP::STAGE >> 4)) | b_lbo;
               const uint32_t a_hi = ((base16 + (w & 0xFFFFu)) | A_LBO) + (X3 ? ks * 256u : 0u);
@@ -699,8 +709,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
             // later: it may not have owned a stage of the last hidden chunks of this unit, so it observes their
             // generation here (each epilogue warp publishes in order: last even + last odd chunk imply the rest).
             const uint32_t nh = u.n_hidden, par = chunk_parity(u.ch[u.last_hidden], s);
-            wait_bar(bar(BAR_CHUNK + nh - 1), par, p.err_flag, 3);
-            wait_bar(bar(BAR_CHUNK + nh - 2), par, p.err_flag, 3);
+            spin_bar(bar(BAR_CHUNK + nh - 1), par);
+            spin_bar(bar(BAR_CHUNK + nh - 2), par);
           }
         }
       }
