@@ -53,7 +53,6 @@ def main():
         for s in range(1, 3):
             print("--- sample %d (clocks rel. to kernel start)" % s)
             print("enc: efree-wait-done %d  E published %d" % (tl[2, s, 0, 0], tl[2, s, 0, 1]))
-            print("unit 2 stages (begin, chunk-ok, full-ok, committed):\n  " + "\n  ".join("%2d: %d +%d +%d +%d" % (k - 1, int(tl[2, s, k, 0]), int(tl[2, s, k, 1] - tl[2, s, k, 0]), int(tl[2, s, k, 2] - tl[2, s, k, 1]), int(tl[2, s, k, 3] - tl[2, s, k, 2])) for k in range(1, 18) if tl[2, s, k, 3]))
             for ui in range(18):
                 if tl[0, s, ui, 3] == 0:
                     break
