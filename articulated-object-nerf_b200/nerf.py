@@ -223,6 +223,9 @@ class _LevelLoop(nn.Module):
         o, d, v = _check_rays(rays)
         R, dev = o.shape[0], o.device
         nc = self.num_coarse_samples + 1
+        if R == 0:      # empty ray batch: nothing to launch (the C ABI rejects null pointers)
+            e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+            return [(e(0, 3), e(0), e(0)), (e(0, 3), e(0), e(0))]
         if randomized:
             if t_rand is None:
                 t_rand = torch.rand(R, nc, device=dev)
