@@ -353,6 +353,8 @@ struct TcParams {
   const float* t_vals;
   long t_stride;
   int R, S, white_bkgd;
+  int seg_len, n_seg;  // samples per CTA (blockIdx.y = segment) and number of segments; n_seg > 1 -> partial results
+  float* partial;      // [n_seg][R][8] = (T, r, g, b, depth, acc, -, -) of each segment, folded by combine_segments_kernel
   float* comp_rgb;
   float* acc;
   float* depth;
@@ -507,7 +509,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = ptx::cluster_ctarank();   // 0 = leader (issues the pair's MMAs), 1 = peer
   const Program& P = p.prog;
-  const int S = p.S;
+  // This CTA composites samples [s0, s0 + S) of its rays (S = local count); SG = samples per ray.
+  const int s0 = (int)blockIdx.y * p.seg_len, SG = p.S;
+  const int S = min(p.seg_len, SG - s0);
   constexpr int NSTAGE = SP::NSTAGE;
   constexpr int E_OFF = off_E(X3), V_OFF = off_V(X3), P_OFF = off_P(X3), ONE_OFF = off_ONE(X3);
 
@@ -565,7 +569,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   auto lbar = [&](int slot) { return lead_bars + 8u * slot; };
   const long long t_start = clock64();
   auto mark = [&](int role, int s, int ui, int ev) {
-    if (p.tl != nullptr && blockIdx.x == 0 && s < 4) p.tl[((role * 4 + s) * MAX_UNITS + ui) * 4 + ev] = clock64() - t_start;
+    if (p.tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && s < 4) p.tl[((role * 4 + s) * MAX_UNITS + ui) * 4 + ev] = clock64() - t_start;
   };
 
   if (warp >= 12) {
@@ -748,11 +752,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     }
     float t[ENC_ROWS];
 #pragma unroll
-    for (int r = 0; r < ENC_ROWS; ++r) t[r] = tv[r][0];
+    for (int r = 0; r < ENC_ROWS; ++r) t[r] = tv[r][s0];
     for (int s = 0; s < S; ++s) {
       float t_next[ENC_ROWS];
 #pragma unroll
-      for (int r = 0; r < ENC_ROWS; ++r) t_next[r] = (s + 1 < S) ? tv[r][s + 1] : 0.f;
+      for (int r = 0; r < ENC_ROWS; ++r) t_next[r] = (s0 + s + 1 < SG) ? tv[r][s0 + s + 1] : 0.f;
       // cast_rays (helper.py:25-26)
       float x[ENC_ROWS][3];
 #pragma unroll
@@ -810,10 +814,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     const float* hw_rgb = hw_sig + 260;
 
     float trans = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cdepth = 0.f, cacc = 0.f;
-    float t_cur = tv[0];
+    float t_cur = tv[s0];
     uint32_t g = 0;
     for (int s = 0; s < S; ++s) {
-      const float t_next = (s + 1 < S) ? tv[s + 1] : 0.f;
+      const float t_next = (s0 + s + 1 < SG) ? tv[s0 + s + 1] : 0.f;
       float sig = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f;  // head accumulators (density; rgb / deformation)
 
       for (int ui = 0; ui < P.n_units; ++ui, ++g) {
@@ -857,7 +861,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_DEMPTY + b));
           }
-          if (p.dbg != nullptr && blockIdx.x == 0 && s == 0) {
+          if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && s == 0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) p.dbg[((size_t)ui * 128 + row) * 256 + cc * 32 + i] = v[i] * (1.0f / SCALE_A);
           }
@@ -941,7 +945,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           bb = __fsub_rn(__fmul_rn(sigmoidf_ref(bb), 1.002f), 0.001f);
           sigma = softplusf_ref(__fadd_rn(raw_sigma, -1.0f));
         }
-        const float delta = (s + 1 < S) ? __fsub_rn(t_next, t_cur) : 1e10f;
+        const float delta = (s0 + s + 1 < SG) ? __fsub_rn(t_next, t_cur) : 1e10f;
         const float dist = __fmul_rn(delta, dnorm);
         const float alpha = __fsub_rn(1.0f, expf(__fmul_rn(-sigma, dist)));
         const float w = __fmul_rn(alpha, trans);
@@ -949,12 +953,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
         cdepth = fmaf(w, t_cur, cdepth);
         cacc += w;
         trans = __fmul_rn(trans, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
-        if (p.weights && valid) p.weights[ray * S + s] = w;
+        if (p.weights && valid) p.weights[ray * SG + s0 + s] = w;   // segment-local weight when n_seg > 1 (scaled later)
       }
       t_cur = t_next;
     }
 
-    if (valid && owner) {
+    if (valid && owner && p.n_seg > 1) {
+      float4* pp = reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.y * p.R + ray) * 8);
+      pp[0] = make_float4(trans, cr, cg, cb);
+      pp[1] = make_float4(cdepth, cacc, 0.f, 0.f);
+    } else if (valid && owner) {
       if (isnan(cdepth)) cdepth = INFINITY;  // helper.py:179 nan_to_num(depth, nan=inf)
       else if (isinf(cdepth)) cdepth = cdepth > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
       if (p.white_bkgd) {
@@ -976,19 +984,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   }
 }
 
+// Folds the per-segment partial composites of one ray in sample order:  C += T * C_seg,  T *= T_seg  (the exclusive
+// transmittance product of helper.py:170-176 re-associated at the segment boundaries), scales the segment-local
+// weights by the transmittance in front of their segment, then applies the final nan/white-background handling.
+__global__ void combine_segments_kernel(const float* __restrict__ partial, int R, int S, int n_seg, int seg_len, int white_bkgd,
+                                        float* __restrict__ comp_rgb, float* __restrict__ acc, float* __restrict__ depth,
+                                        float* __restrict__ weights) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= R) return;
+  float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, ca = 0.f;
+  for (int g = 0; g < n_seg; ++g) {
+    const float4 a = *reinterpret_cast<const float4*>(partial + ((size_t)g * R + ray) * 8);
+    const float4 b = *reinterpret_cast<const float4*>(partial + ((size_t)g * R + ray) * 8 + 4);
+    cr = fmaf(T, a.y, cr); cg = fmaf(T, a.z, cg); cb = fmaf(T, a.w, cb);
+    cd = fmaf(T, b.x, cd); ca = fmaf(T, b.y, ca);
+    if (weights != nullptr && g > 0) {
+      const int e = min(S, (g + 1) * seg_len);
+      for (int s = g * seg_len; s < e; ++s) weights[(size_t)ray * S + s] *= T;
+    }
+    T *= a.x;
+  }
+  if (isnan(cd)) cd = INFINITY;
+  else if (isinf(cd)) cd = cd > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+  if (white_bkgd) {
+    const float bg = __fsub_rn(1.0f, ca);
+    cr += bg; cg += bg; cb += bg;
+  }
+  comp_rgb[3 * (size_t)ray + 0] = cr; comp_rgb[3 * (size_t)ray + 1] = cg; comp_rgb[3 * (size_t)ray + 2] = cb;
+  acc[ray] = ca;
+  depth[ray] = cd;
+}
+
+// Samples-per-CTA split: small ray batches (the reference's 3840-ray chunks = 15 CTA pairs on 74 pair slots) leave most
+// SMs idle; cutting each ray's sample range into n segments gives n times as many CTAs.  Cost model per wave:
+// ceil(S / n) sample planes + ~3 planes of start-up (view encoding, pipeline fill, combine).
+static int choose_segments(int pairs, int S, int pair_slots) {
+  int best = 1;
+  long best_cost = -1;
+  for (int n = 1; n <= 16 && n <= S / 4; ++n) {
+    const long waves = ((long)pairs * n + pair_slots - 1) / pair_slots;
+    const long cost = waves * ((S + n - 1) / n + 3);
+    if (best_cost < 0 || cost * 100 < best_cost * 90) { best = n; best_cost = cost; }   // needs a > 10 % win over fewer segments
+  }
+  return best;
+}
+
 // ---- host side -------------------------------------------------------------------------------------------
 static float* g_dbg = nullptr;
+static int g_force_segments = 0;   // debug hook: > 0 forces the number of sample segments per ray
 static int* g_err = nullptr;
 static long long* g_tl = nullptr;
 
 template <int KIND, bool X3, bool BF16>
-static int launch(const TcParams& p, int grid, cudaStream_t st) {
+static int launch(const TcParams& p, int grid, int grid_y, cudaStream_t st) {
   using SP = SmemPlan<KIND, X3>;
   auto kern = render_tc_kernel<KIND, X3, BF16>;
   AON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)grid);
+  cfg.gridDim = dim3((unsigned)grid, (unsigned)grid_y);
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = SP::TOTAL;
   cfg.stream = st;
@@ -1027,17 +1081,51 @@ int render_level_tc(int kind, int precision, const void* packed, const float* fo
   p.err_flag = g_err;
   p.tl = g_tl;
   const int grid = ((R + 255) / 256) * 2;   // CTA pairs; an odd last tile leaves the peer with no valid rays
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_seg = g_force_segments > 0 ? (g_force_segments <= S ? g_force_segments : 1) : choose_segments(grid / 2, S, sms / 2);
+  p.n_seg = n_seg;
+  p.seg_len = (S + n_seg - 1) / n_seg;
+  p.partial = nullptr;
+  if (n_seg > 1) {
+    // stream-ordered temporary for the per-segment partial composites (released right after the combine kernel).
+    // The default pool hands freed memory back to the driver at every synchronisation (a real cudaMalloc, ~1 ms, on the
+    // next call): keep it cached.
+    static bool pool_tuned[64] = {false};
+    if (dev < 64 && !pool_tuned[dev]) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_tuned[dev] = true;
+    }
+    AON_CUDA_CHECK(cudaMallocAsync((void**)&p.partial, (size_t)n_seg * R * 8 * sizeof(float), st));
+  }
   const bool van = kind == AON_KIND_VANILLA;
+  int rc = AON_E_ARG;
   switch (precision) {
     case AON_PREC_TC_F16X3:
-      return van ? launch<AON_KIND_VANILLA, true, false>(p, grid, st) : launch<AON_KIND_AUTODECODER, true, false>(p, grid, st);
+      rc = van ? launch<AON_KIND_VANILLA, true, false>(p, grid, n_seg, st) : launch<AON_KIND_AUTODECODER, true, false>(p, grid, n_seg, st);
+      break;
     case AON_PREC_TC_F16:
-      return van ? launch<AON_KIND_VANILLA, false, false>(p, grid, st) : launch<AON_KIND_AUTODECODER, false, false>(p, grid, st);
+      rc = van ? launch<AON_KIND_VANILLA, false, false>(p, grid, n_seg, st) : launch<AON_KIND_AUTODECODER, false, false>(p, grid, n_seg, st);
+      break;
     case AON_PREC_TC_BF16:
-      return van ? launch<AON_KIND_VANILLA, false, true>(p, grid, st) : launch<AON_KIND_AUTODECODER, false, true>(p, grid, st);
+      rc = van ? launch<AON_KIND_VANILLA, false, true>(p, grid, n_seg, st) : launch<AON_KIND_AUTODECODER, false, true>(p, grid, n_seg, st);
+      break;
+    default:
+      set_error("bad precision %d", precision);
   }
-  set_error("bad precision %d", precision);
-  return AON_E_ARG;
+  if (n_seg > 1) {
+    if (rc == AON_OK) {
+      combine_segments_kernel<<<(R + 255) / 256, 256, 0, st>>>(p.partial, R, S, n_seg, p.seg_len, white_bkgd, comp_rgb, acc, depth, weights);
+      g_launches++;
+      if (cudaGetLastError() != cudaSuccess) { set_error("combine_segments_kernel launch failed"); rc = AON_E_CUDA; }
+    }
+    cudaFreeAsync(p.partial, st);
+  }
+  return rc;
 }
 
 int pack_tail(int kind, const PackedLayout& L, const float* const* w, const float* const* b, char* packed,
@@ -1081,6 +1169,7 @@ extern "C" void aon_debug_set_buffers(float* dbg_dev, int* err_dev) {
   g_err = err_dev;
 }
 extern "C" void aon_debug_set_timeline(long long* tl_dev) { g_tl = tl_dev; }
+extern "C" void aon_debug_force_segments(int n) { g_force_segments = n; }
 extern "C" int aon_debug_program_info(int kind, int precision, int* n_units, int* n_stages, int* smem_bytes) {
   const Program P = build_program(kind, precision);
   if (n_units) *n_units = P.n_units;

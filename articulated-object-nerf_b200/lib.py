@@ -238,3 +238,12 @@ def debug_set_timeline(tl: Optional[torch.Tensor]) -> None:
     lib.aon_debug_set_timeline.restype = None
     lib.aon_debug_set_timeline.argtypes = [_vp]
     lib.aon_debug_set_timeline(None if tl is None else tl.data_ptr())
+
+
+def debug_force_segments(n: int) -> None:
+    """n > 0: every tensor-core render_level call cuts each ray's sample range into n segments (one CTA pair per ray tile
+    and segment, partial composites folded by a combine kernel); 0: automatic choice (small ray batches only)."""
+    lib = load()
+    lib.aon_debug_force_segments.restype = None
+    lib.aon_debug_force_segments.argtypes = [_i]
+    lib.aon_debug_force_segments(int(n))

@@ -115,3 +115,30 @@ def test_full_size_properties(ctx):
     t1 = lib.sample_pdf(t0, w0, 128)
     assert (t1[:, 1:] >= t1[:, :-1]).all() and t1.min() >= 2.0 and t1.max() <= 6.0
     assert (w0 >= 0).all() and torch.allclose(w0.sum(-1), full[0][1], atol=1e-5)
+
+
+@pytest.mark.parametrize("nseg", [0, 1, 3, 7])
+def test_sample_segments_match_oracle(ctx, nseg):
+    """Small ray batches are spread over the SMs by cutting every ray's sample range into segments (one CTA pair per
+    tile and segment + a combine kernel).  0 = automatic choice.  Both levels, incl. the per-sample weights, against
+    the oracle; the segment count must not change the result beyond re-association noise."""
+    lib, net, sd, dev = ctx
+    rays = O.sapien_rays(15, 20, seed=6)                  # 300 rays: 2 CTA pairs, ragged
+    rd = {k: v.to(dev) for k, v in rays.items()}
+    want = O.nerf_forward(sd, rays, False, True, 2.0, 6.0)
+    pc = net._cache["coarse"].get(net.coarse_mlp, net.precision)
+    t0 = lib.sample_along_rays(2.0, 6.0, 65, 300, dev)
+    lib.debug_force_segments(1)
+    ref = lib.render_level(0, net.precision, pc, None, rd["rays_o"], rd["rays_d"], rd["viewdirs"], t0, True, True)
+    lib.debug_force_segments(nseg)
+    try:
+        with torch.no_grad():
+            got = net(rd, False, True, 2.0, 6.0)
+        seg = lib.render_level(0, net.precision, pc, None, rd["rays_o"], rd["rays_d"], rd["viewdirs"], t0, True, True)
+    finally:
+        lib.debug_force_segments(0)
+    for lv in range(2):
+        for j in range(3):
+            assert relerr(got[lv][j].cpu(), want[lv][j]) < 1e-4, (nseg, lv, j)
+    for a, b in zip(seg, ref):                              # rgb, acc, depth, weights [R,65] of the coarse level
+        assert (a - b).abs().max() < 2e-6
