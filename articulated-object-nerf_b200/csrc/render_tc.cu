@@ -1032,6 +1032,7 @@ static int choose_segments(int pairs, int S, int pair_slots) {
 // ---- host side -------------------------------------------------------------------------------------------
 static float* g_dbg = nullptr;
 static int g_force_segments = 0;   // debug hook: > 0 forces the number of sample segments per ray
+static int g_no_tail_split = 0;    // debug hook: 1 = never split the last wave of a large batch
 static int* g_err = nullptr;
 static long long* g_tl = nullptr;
 
@@ -1058,32 +1059,11 @@ static int launch(const TcParams& p, int grid, int grid_y, cudaStream_t st) {
   return AON_OK;
 }
 
-int render_level_tc(int kind, int precision, const void* packed, const float* folded, const float* rays_o,
-                    const float* rays_d, const float* viewdirs, const float* t_vals, long t_stride, int R, int S,
-                    int white_bkgd, float* comp_rgb, float* acc, float* depth, float* weights, cudaStream_t st) {
-  int dev = 0, major = 0;
-  AON_CUDA_CHECK(cudaGetDevice(&dev));
-  AON_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
-  if (major != 10) {
-    set_error("tensor-core precision modes need an sm_100 device (found compute capability %d.x)", major);
-    return AON_E_UNSUPPORTED;
-  }
-  TcParams p;
-  p.prog = build_program(kind, precision);
-  p.L = layout_tc(kind, precision);
-  p.packed = (const char*)packed;
-  p.folded = folded;
-  p.rays_o = rays_o; p.rays_d = rays_d; p.viewdirs = viewdirs;
-  p.t_vals = t_vals; p.t_stride = t_stride;
-  p.R = R; p.S = S; p.white_bkgd = white_bkgd;
-  p.comp_rgb = comp_rgb; p.acc = acc; p.depth = depth; p.weights = weights;
-  p.dbg = g_dbg;
-  p.err_flag = g_err;
-  p.tl = g_tl;
+// Renders rays [0, R) of the arrays in `p` (already offset by the caller) with n_seg sample segments per ray.
+static int render_range(TcParams p, int kind, int precision, int R, int n_seg, int dev, cudaStream_t st) {
+  const int S = p.S;
+  p.R = R;
   const int grid = ((R + 255) / 256) * 2;   // CTA pairs; an odd last tile leaves the peer with no valid rays
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int n_seg = g_force_segments > 0 ? (g_force_segments <= S ? g_force_segments : 1) : choose_segments(grid / 2, S, sms / 2);
   p.n_seg = n_seg;
   p.seg_len = (S + n_seg - 1) / n_seg;
   p.partial = nullptr;
@@ -1119,13 +1099,56 @@ int render_level_tc(int kind, int precision, const void* packed, const float* fo
   }
   if (n_seg > 1) {
     if (rc == AON_OK) {
-      combine_segments_kernel<<<(R + 255) / 256, 256, 0, st>>>(p.partial, R, S, n_seg, p.seg_len, white_bkgd, comp_rgb, acc, depth, weights);
+      combine_segments_kernel<<<(R + 255) / 256, 256, 0, st>>>(p.partial, R, S, n_seg, p.seg_len, p.white_bkgd, p.comp_rgb, p.acc, p.depth, p.weights);
       g_launches++;
       if (cudaGetLastError() != cudaSuccess) { set_error("combine_segments_kernel launch failed"); rc = AON_E_CUDA; }
     }
     cudaFreeAsync(p.partial, st);
   }
   return rc;
+}
+
+int render_level_tc(int kind, int precision, const void* packed, const float* folded, const float* rays_o,
+                    const float* rays_d, const float* viewdirs, const float* t_vals, long t_stride, int R, int S,
+                    int white_bkgd, float* comp_rgb, float* acc, float* depth, float* weights, cudaStream_t st) {
+  int dev = 0, major = 0;
+  AON_CUDA_CHECK(cudaGetDevice(&dev));
+  AON_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("tensor-core precision modes need an sm_100 device (found compute capability %d.x)", major);
+    return AON_E_UNSUPPORTED;
+  }
+  TcParams p;
+  p.prog = build_program(kind, precision);
+  p.L = layout_tc(kind, precision);
+  p.packed = (const char*)packed;
+  p.folded = folded;
+  p.rays_o = rays_o; p.rays_d = rays_d; p.viewdirs = viewdirs;
+  p.t_vals = t_vals; p.t_stride = t_stride;
+  p.R = R; p.S = S; p.white_bkgd = white_bkgd;
+  p.comp_rgb = comp_rgb; p.acc = acc; p.depth = depth; p.weights = weights;
+  p.dbg = g_dbg;
+  p.err_flag = g_err;
+  p.tl = g_tl;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int pairs = (R + 255) / 256, slots = sms / 2;
+  if (g_force_segments > 0) return render_range(p, kind, precision, R, g_force_segments <= S ? g_force_segments : 1, dev, st);
+  if (pairs <= slots || g_no_tail_split) return render_range(p, kind, precision, R, choose_segments(pairs, S, slots), dev, st);
+  // Large batch = several waves of ray tiles over the pair slots.  The last, partly filled wave (640x480: 1200 tiles on 74
+  // slots = 16.2 waves) would hold all but a few SMs idle for a whole tile time: render the full waves unsplit and the
+  // remainder tiles in a second launch with sample segments, so the remainder spreads over every SM.
+  const int rem = pairs % slots;
+  const int n_tail = rem ? choose_segments(rem, S, slots) : 1;
+  if (n_tail == 1) return render_range(p, kind, precision, R, 1, dev, st);
+  const int R_main = (pairs - rem) * 256;
+  int rc = render_range(p, kind, precision, R_main, 1, dev, st);
+  if (rc != AON_OK) return rc;
+  p.rays_o += 3 * (size_t)R_main; p.rays_d += 3 * (size_t)R_main; p.viewdirs += 3 * (size_t)R_main;
+  p.t_vals += (size_t)R_main * t_stride;
+  p.comp_rgb += 3 * (size_t)R_main; p.acc += R_main; p.depth += R_main;
+  if (p.weights) p.weights += (size_t)R_main * S;
+  return render_range(p, kind, precision, R - R_main, n_tail, dev, st);
 }
 
 int pack_tail(int kind, const PackedLayout& L, const float* const* w, const float* const* b, char* packed,
@@ -1170,6 +1193,7 @@ extern "C" void aon_debug_set_buffers(float* dbg_dev, int* err_dev) {
 }
 extern "C" void aon_debug_set_timeline(long long* tl_dev) { g_tl = tl_dev; }
 extern "C" void aon_debug_force_segments(int n) { g_force_segments = n; }
+extern "C" void aon_debug_no_tail_split(int on) { g_no_tail_split = on; }
 extern "C" int aon_debug_program_info(int kind, int precision, int* n_units, int* n_stages, int* smem_bytes) {
   const Program P = build_program(kind, precision);
   if (n_units) *n_units = P.n_units;

@@ -247,3 +247,12 @@ def debug_force_segments(n: int) -> None:
     lib.aon_debug_force_segments.restype = None
     lib.aon_debug_force_segments.argtypes = [_i]
     lib.aon_debug_force_segments(int(n))
+
+
+def debug_no_tail_split(on: bool) -> None:
+    """True: large ray batches are rendered by ONE unsplit launch per level (the behaviour before the last, partly filled
+    wave of ray tiles got its own sample-segmented launch).  For A/B timing and parity tests only."""
+    lib = load()
+    lib.aon_debug_no_tail_split.restype = None
+    lib.aon_debug_no_tail_split.argtypes = [_i]
+    lib.aon_debug_no_tail_split(1 if on else 0)

@@ -142,3 +142,33 @@ def test_sample_segments_match_oracle(ctx, nseg):
             assert relerr(got[lv][j].cpu(), want[lv][j]) < 1e-4, (nseg, lv, j)
     for a, b in zip(seg, ref):                              # rgb, acc, depth, weights [R,65] of the coarse level
         assert (a - b).abs().max() < 2e-6
+
+
+def test_tail_wave_split_matches_unsplit(ctx):
+    """A batch of more ray tiles than CTA-pair slots renders its last, partly filled wave in a second launch with
+    sample segments.  Same per-ray arithmetic up to the re-association at segment boundaries: compare with the
+    single unsplit launch (both levels, per-sample coarse weights included)."""
+    lib, net, sd, dev = ctx
+    slots = torch.cuda.get_device_properties(dev).multi_processor_count // 2
+    R = slots * 256 + 300                                   # one full wave + 2 ragged remainder tiles
+    rays = O.sapien_rays(120, 200, seed=9)
+    rd = {k: v[:R].contiguous().to(dev) for k, v in rays.items()}
+    assert rd["rays_o"].shape[0] == R
+    pc = net._cache["coarse"].get(net.coarse_mlp, net.precision)
+    t0 = lib.sample_along_rays(2.0, 6.0, 65, R, dev)
+    lib.debug_no_tail_split(True)
+    try:
+        with torch.no_grad():
+            ref_full = net(rd, False, True, 2.0, 6.0)
+        ref = lib.render_level(0, net.precision, pc, None, rd["rays_o"], rd["rays_d"], rd["viewdirs"], t0, True, True)
+    finally:
+        lib.debug_no_tail_split(False)
+    with torch.no_grad():
+        got_full = net(rd, False, True, 2.0, 6.0)
+    got = lib.render_level(0, net.precision, pc, None, rd["rays_o"], rd["rays_d"], rd["viewdirs"], t0, True, True)
+    for j, (a, b) in enumerate(zip(got, ref)):             # rgb, acc, depth (values up to far = 6), weights [R,65]
+        assert (a - b).abs().max() < 1e-5, (j, (a - b).abs().max().item())   # re-association at up to 16 segment boundaries
+        assert torch.equal(a[:slots * 256], b[:slots * 256]) or (a[:slots * 256] - b[:slots * 256]).abs().max() < 2e-6
+    for lv in range(2):
+        for j in range(3):
+            assert relerr(got_full[lv][j].cpu(), ref_full[lv][j].cpu()) < 1e-4, (lv, j)
