@@ -21,7 +21,7 @@ PREC_FP32, PREC_TC_F16X3, PREC_TC_F16, PREC_TC_BF16 = 0, 1, 2, 3
 PRECISIONS = {"fp32": PREC_FP32, "f16x3": PREC_TC_F16X3, "f16": PREC_TC_F16, "bf16": PREC_TC_BF16}
 
 # every symbol include/aon.h declares: name -> (restype, argtypes)
-_vp, _fp, _i, _l, _f, _sz = C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_size_t
+_vp, _fp, _i, _l, _f, _sz, _d = C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_size_t, C.c_double
 SYMBOLS = {
     "aon_version": (_i, []),
     "aon_last_error": (C.c_char_p, []),
@@ -36,6 +36,11 @@ SYMBOLS = {
     "aon_render_level": (_i, [_i, _i, _vp, _fp, _fp, _fp, _fp, _fp, _l, _i, _i, _i, _fp, _fp, _fp, _fp, _vp]),
     "aon_sample_pdf": (_i, [_fp, _l, _fp, _fp, _l, _i, _i, _i, _fp, _vp]),
     "aon_render_image_host": (_i, [_i, _i, _vp, _vp, _fp, _fp, _fp, _fp, _fp, _i, _f, _f, _i, _fp, _fp, _vp]),
+    "aon_pos_enc": (_i, [_fp, _l, _i, _fp, _vp]),
+    "aon_pos_enc_backward": (_i, [_fp, _fp, _l, _i, _fp, _vp]),
+    "aon_composite": (_i, [_fp, _fp, _fp, _l, _fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _vp]),
+    "aon_composite_backward": (_i, [_fp, _fp, _fp, _l, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),
+    "aon_adam_step": (_i, [_fp, _fp, _fp, _fp, _l, _d, _d, _d, _d, _l, _d, _vp]),
     "aon_launch_count": (_l, [_i]),
 }
 
@@ -209,6 +214,67 @@ def render_image_host(kind: int, precision: int, packed_coarse, packed_fine, fol
                                          None if coarse_out is None else coarse_out.data_ptr(), _stream()),
                "aon_render_image_host")
     return out
+
+
+# ---- training path, stage 1: per-element stages with hand-written adjoints (csrc/train_ops.cu) ----------
+def pos_enc(x: torch.Tensor, max_deg: int) -> torch.Tensor:
+    """helper.py:136-140 with min_deg = 0: x [..., 3] -> [..., 3 + 6 max_deg]."""
+    lib = load()
+    n = x.numel() // 3
+    out = torch.empty(tuple(x.shape[:-1]) + (3 + 6 * max_deg,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib.aon_pos_enc(_ptr(x, "x"), n, max_deg, _ptr(out), _stream()), "aon_pos_enc")
+    return out
+
+
+def pos_enc_backward(x: torch.Tensor, g_out: torch.Tensor, max_deg: int) -> torch.Tensor:
+    lib = load()
+    gx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _check(lib.aon_pos_enc_backward(_ptr(x, "x"), _ptr(g_out, "g_out"), x.numel() // 3, max_deg, _ptr(gx), _stream()),
+               "aon_pos_enc_backward")
+    return gx
+
+
+def composite(raw_rgb: torch.Tensor, raw_sigma: torch.Tensor, t_vals: torch.Tensor, dirs: torch.Tensor, white_bkgd: bool,
+              act_mode: int):
+    """Activations + volumetric_rendering of raw MLP outputs [R,S,3] / [R,S].  Returns (comp_rgb, acc, depth, weights,
+    trans); trans [R,S] is the exclusive transmittance the backward needs."""
+    lib = load()
+    R, S = raw_sigma.shape[0], raw_sigma.shape[1]
+    dev = raw_rgb.device
+    stride = 0 if t_vals.dim() == 1 else S
+    e = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
+    rgb, acc, depth, w, tr = e(R, 3), e(R), e(R), e(R, S), e(R, S)
+    with torch.cuda.device(dev):
+        _check(lib.aon_composite(_ptr(raw_rgb, "raw_rgb"), _ptr(raw_sigma, "raw_sigma"), _ptr(t_vals, "t_vals"), stride,
+                                 _ptr(dirs, "dirs"), R, S, int(bool(white_bkgd)), act_mode, _ptr(rgb), _ptr(acc), _ptr(depth),
+                                 _ptr(w), _ptr(tr), _stream()), "aon_composite")
+    return rgb, acc, depth, w, tr
+
+
+def composite_backward(raw_rgb, raw_sigma, t_vals, dirs, weights, trans, g_rgb, g_acc, g_depth, white_bkgd: bool, act_mode: int):
+    lib = load()
+    R, S = raw_sigma.shape[0], raw_sigma.shape[1]
+    stride = 0 if t_vals.dim() == 1 else S
+    g_raw_rgb, g_raw_sigma = torch.empty_like(raw_rgb), torch.empty_like(raw_sigma)
+    with torch.cuda.device(raw_rgb.device):
+        _check(lib.aon_composite_backward(_ptr(raw_rgb, "raw_rgb"), _ptr(raw_sigma, "raw_sigma"), _ptr(t_vals, "t_vals"), stride,
+                                          _ptr(dirs, "dirs"), _ptr(weights, "weights"), _ptr(trans, "trans"),
+                                          _ptr(g_rgb, "g_rgb"), _ptr(g_acc, "g_acc"), _ptr(g_depth, "g_depth"), R, S,
+                                          int(bool(white_bkgd)), act_mode, _ptr(g_raw_rgb), _ptr(g_raw_sigma), _stream()),
+               "aon_composite_backward")
+    return g_raw_rgb, g_raw_sigma
+
+
+def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float,
+              beta1: float, beta2: float, eps: float, step: int, grad_scale: float = 1.0) -> None:
+    """One Adam step over flat fp32 buffers, in place (torch.optim.Adam formulas)."""
+    lib = load()
+    with torch.cuda.device(params.device):
+        _check(lib.aon_adam_step(_ptr(params, "params"), _ptr(grads, "grads"), _ptr(exp_avg, "exp_avg"),
+                                 _ptr(exp_avg_sq, "exp_avg_sq"), params.numel(), float(lr), float(beta1), float(beta2),
+                                 float(eps), int(step), float(grad_scale), _stream()), "aon_adam_step")
 
 
 # ---- debug hooks (exported by the library but deliberately not part of include/aon.h) ------------------

@@ -29,6 +29,7 @@ import torch
 import torch.nn as nn
 
 from . import dist as D
+from . import lib as L
 from .nerf import CodeLibraryArticulated, NeRF, NeRF_AE_Art, img2mse, mse2psnr
 
 Tensor = torch.Tensor
@@ -81,6 +82,67 @@ def write_stats(fpath, *stats):
         json.dump(d, fp, indent=4, sort_keys=True)
 
 
+class FlatAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(betas, eps, no weight decay) semantics (model.py:386-389) on ONE flat fp32 buffer:
+    the parameters and their .grad become views of two contiguous device buffers, so the gradient all-reduce
+    (dist.allreduce_mean_) needs no gather/scatter copies and the update is one aon_adam_step launch instead of
+    a per-tensor loop.  ``param_groups[0]['lr']`` is honoured every step (optimizer_step writes the schedule there)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        params = [p for p in params if p.requires_grad]
+        if not params or not all(p.is_cuda and p.dtype == torch.float32 for p in params):
+            raise L.AonError("FlatAdam needs CUDA float32 parameters (move the module to the GPU first): no CPU fallback")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        ps = self.param_groups[0]["params"]
+        n, dev = sum(p.numel() for p in ps), ps[0].device
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.steps, self.grad_scale = 0, 1.0
+        off = 0
+        with torch.no_grad():
+            for p in ps:
+                k = p.numel()
+                self.flat[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat[off:off + k].view(p.shape)
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+                off += k
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.flat_grad.zero_()
+        off = 0
+        for p in self.param_groups[0]["params"]:       # re-attach if someone dropped the view (p.grad = None)
+            k = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+            off += k
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        g = self.param_groups[0]
+        self.steps += 1
+        L.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1],
+                    g["eps"], self.steps, self.grad_scale)
+        for p in g["params"]:                           # the kernel wrote through raw pointers: tell autograd / the
+            torch.autograd.graph.increment_version(p)   # packed-weight cache that the values changed
+        return loss
+
+    def state_dict(self):
+        return {"steps": self.steps, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+
+    def load_state_dict(self, sd):
+        self.steps = int(sd["steps"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.param_groups[0].update(sd["param_groups"][0])
+
+
 class _LitCommon(LitModel):
     near, far, white_bkgd = 2.0, 6.0, True     # datasets/sapien.py:72-73 constants; setup() may override
 
@@ -102,7 +164,8 @@ class _LitCommon(LitModel):
 
     # ---- optimisation (model.py:386-419) ----
     def configure_optimizers(self):
-        return torch.optim.Adam(params=self.parameters(), lr=self.lr_init, betas=(0.9, 0.999))
+        """Adam(lr_init, betas (0.9, 0.999)) like model.py:386-389, as the flat-buffer aon_adam_step optimizer."""
+        return FlatAdam(self.parameters(), lr=self.lr_init, betas=(0.9, 0.999))
 
     def learning_rate(self, step: int) -> float:
         if self.lr_delay_steps > 0:
@@ -274,8 +337,8 @@ class Trainer:
 
     def fit(self, system: _LitCommon, batches) -> _LitCommon:
         system.trainer = self
-        opt = system.configure_optimizers()
-        params = [p for p in system.parameters() if p.requires_grad]
+        opt = getattr(system, "_optimizer", None) or system.configure_optimizers()
+        system._optimizer = opt                          # Adam moments survive repeated fit() calls
         system.train()
         for batch_idx, batch in enumerate(batches):
             if self.global_step >= self.max_steps:
@@ -284,14 +347,7 @@ class Trainer:
             loss = system.training_step(batch, batch_idx)
             loss.backward()
             if D.world()[1] > 1:
-                flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
-                D.allreduce_mean_(flat)
-                off = 0
-                for p in params:
-                    n = p.numel()
-                    if p.grad is not None:
-                        p.grad.copy_(flat[off:off + n].view_as(p))
-                    off += n
+                D.allreduce_mean_(opt.flat_grad)         # the gradients already live in one flat buffer
             system.optimizer_step(0, batch_idx, opt, 0, None, False, False, False)
             self.global_step += 1
             if self.log_every and self.is_global_zero and self.global_step % self.log_every == 0:

@@ -139,7 +139,7 @@ class NeRFMLP_AE(nn.Module):
         for lin in self.deformations_linear:
             h = F.relu(lin(h))
         warped = self.deformation_layer(h) + x0
-        h = torch.cat([pos_enc_torch(warped, 0, 10), shape], -1)
+        h = torch.cat([pos_enc_cuda(warped, 0, 10), shape], -1)
         inputs = h
         for i, lin in enumerate(self.pts_linears):
             h = F.relu(lin(h))
@@ -154,25 +154,54 @@ class NeRFMLP_AE(nn.Module):
         return self.rgb_layer(h).reshape(-1, S, 3), raw_density
 
 
-def pos_enc_torch(x: Tensor, min_deg: int, max_deg: int) -> Tensor:
-    """helper.py:136-140 in torch ops (autograd training path only)."""
-    scales = torch.tensor([2 ** i for i in range(min_deg, max_deg)], dtype=x.dtype, device=x.device)
-    xb = (x[..., None, :] * scales[:, None]).reshape(list(x.shape[:-1]) + [-1])
-    return torch.cat([x, torch.sin(torch.cat([xb, xb + 0.5 * np.pi], -1))], -1)
+class _PosEncFn(torch.autograd.Function):
+    """helper.py:136-140 (min_deg 0) through aon_pos_enc, adjoint through aon_pos_enc_backward."""
+
+    @staticmethod
+    def forward(ctx, x, max_deg):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        ctx.max_deg = max_deg
+        return L.pos_enc(x, max_deg)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return L.pos_enc_backward(x, g.contiguous(), ctx.max_deg), None
 
 
-def volumetric_rendering_torch(rgb, density, t_vals, dirs, white_bkgd):
-    """helper.py:157-195 in torch ops (autograd training path only)."""
-    dists = torch.cat([t_vals[..., 1:] - t_vals[..., :-1], torch.full_like(t_vals[..., :1], 1e10)], -1)
-    dists = dists * torch.norm(dirs[..., None, :], dim=-1)
-    alpha = 1.0 - torch.exp(-density[..., 0] * dists)
-    trans = torch.cat([torch.ones_like(alpha[..., :1]), torch.cumprod(1.0 - alpha[..., :-1] + 1e-10, -1)], -1)
-    w = alpha * trans
-    comp = (w[..., None] * rgb).sum(-2)
-    depth = torch.nan_to_num((w * t_vals).sum(-1), float("inf"))
-    acc = w.sum(-1)
-    if white_bkgd:
-        comp = comp + (1.0 - acc[..., None])
+def pos_enc_cuda(x: Tensor, min_deg: int, max_deg: int) -> Tensor:
+    if min_deg != 0:
+        raise L.AonError("pos_enc: the reference only ever uses min_deg = 0")
+    return _PosEncFn.apply(x, max_deg) if x.requires_grad else L.pos_enc(x.contiguous(), max_deg)
+
+
+class _CompositeFn(torch.autograd.Function):
+    """Activations (model.py:186-187 / model_autodecoder.py:321-323) + volumetric_rendering (helper.py:157-195) through
+    aon_composite; adjoint w.r.t. the raw MLP outputs through aon_composite_backward.  t_vals and dirs carry no
+    gradient (the reference detaches the samples, helper.py:249; rays are data)."""
+
+    @staticmethod
+    def forward(ctx, raw_rgb, raw_sigma, t_vals, dirs, white_bkgd, act_mode):
+        raw_rgb, raw_sigma = raw_rgb.contiguous(), raw_sigma.contiguous()
+        comp, acc, depth, w, trans = L.composite(raw_rgb, raw_sigma, t_vals, dirs, white_bkgd, act_mode)
+        ctx.save_for_backward(raw_rgb, raw_sigma, t_vals, dirs, w, trans)
+        ctx.cfg = (white_bkgd, act_mode)
+        ctx.mark_non_differentiable(w)
+        return comp, acc, depth, w
+
+    @staticmethod
+    def backward(ctx, g_comp, g_acc, g_depth, _g_w):
+        raw_rgb, raw_sigma, t_vals, dirs, w, trans = ctx.saved_tensors
+        c = lambda g: None if g is None else g.contiguous()
+        g_rgb, g_sigma = L.composite_backward(raw_rgb, raw_sigma, t_vals, dirs, w, trans, c(g_comp), c(g_acc), c(g_depth),
+                                              *ctx.cfg)
+        return g_rgb, g_sigma, None, None, None, None
+
+
+def composite_cuda(raw_rgb, raw_sigma, t_vals, dirs, white_bkgd, act_mode):
+    """raw_rgb [R,S,3], raw_sigma [R,S,1] -> (comp_rgb, acc, weights, depth) like helper.volumetric_rendering."""
+    comp, acc, depth, w = _CompositeFn.apply(raw_rgb, raw_sigma.reshape(raw_sigma.shape[0], -1), t_vals, dirs, bool(white_bkgd), act_mode)
     return comp, acc, w, depth
 
 
@@ -254,7 +283,7 @@ class _LevelLoop(nn.Module):
         R = o.shape[0]
         ret = []
         t_vals = t0 if t0.dim() == 2 else t0[None, :].expand(R, -1).contiguous()
-        view_enc = pos_enc_torch(v, 0, 4)
+        view_enc = pos_enc_cuda(v, 0, 4)
         weights = None
         for level, mlp in enumerate((self.coarse_mlp, self.fine_mlp)):
             if level == 1:
@@ -262,13 +291,10 @@ class _LevelLoop(nn.Module):
                                       u=None if u is None else u.contiguous())
             samples = o[:, None, :] + t_vals[..., None] * d[:, None, :]
             if latents is None:
-                raw_rgb, raw_sigma = mlp(pos_enc_torch(samples, 0, 10), view_enc)
-                rgb, sigma = torch.sigmoid(raw_rgb), F.relu(raw_sigma)
+                raw_rgb, raw_sigma = mlp(pos_enc_cuda(samples, 0, 10), view_enc)
             else:
                 raw_rgb, raw_sigma = mlp(samples, view_enc, latents)
-                rgb = torch.sigmoid(raw_rgb) * (1 + 2 * 0.001) - 0.001
-                sigma = F.softplus(raw_sigma + (-1.0))
-            comp, acc, weights, depth = volumetric_rendering_torch(rgb, sigma, t_vals, d, white_bkgd)
+            comp, acc, weights, depth = composite_cuda(raw_rgb, raw_sigma, t_vals, d, white_bkgd, 0 if latents is None else 1)
             ret.append((comp, acc, depth))
         return ret
 

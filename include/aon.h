@@ -130,6 +130,39 @@ int aon_render_image_host(int kind, int precision, const void* packed_coarse,
                           float far, int white_bkgd, float* out_host, float* coarse_out_host,
                           aon_stream_t stream);
 
+/* ---- training path, stage 1: per-element stages with hand-written adjoints ------------
+ * The MLP contractions of training_step stay library GEMMs for now; these entry points replace every
+ * elementwise / per-ray torch op around them and their autograd adjoints.
+ *
+ * aon_pos_enc / _backward: pos_enc(x, 0, max_deg) of helper.py:136-140 for x [n,3] -> out [n, 3+6*max_deg]
+ * and its adjoint g_x [n,3] (needed by the auto-decoder, whose encoded position depends on the
+ * deformation MLP, model_autodecoder.py:203-207). */
+int aon_pos_enc(const float* x, long n, int max_deg, float* out, aon_stream_t stream);
+int aon_pos_enc_backward(const float* x, const float* g_out, long n, int max_deg, float* g_x,
+                         aon_stream_t stream);
+
+/* aon_composite / _backward: activations (model.py:186-187; act_mode 1 = model_autodecoder.py:321-323)
+ * + volumetric_rendering (helper.py:157-195) of MLP outputs raw_rgb [R,S,3], raw_sigma [R,S] ->
+ * comp_rgb [R,3], acc [R], depth [R], weights [R,S] (may be NULL), trans [R,S] (exclusive transmittance;
+ * may be NULL, needed by the backward).  The backward takes dL/dcomp_rgb (and optionally dL/dacc,
+ * dL/ddepth; NULL = zero) and returns dL/draw_rgb [R,S,3], dL/draw_sigma [R,S]; t_vals carry no gradient
+ * (the reference detaches the samples, helper.py:249). */
+int aon_composite(const float* raw_rgb, const float* raw_sigma, const float* t_vals, long t_stride,
+                  const float* dirs, int R, int S, int white_bkgd, int act_mode, float* comp_rgb,
+                  float* acc, float* depth, float* weights, float* trans, aon_stream_t stream);
+int aon_composite_backward(const float* raw_rgb, const float* raw_sigma, const float* t_vals,
+                           long t_stride, const float* dirs, const float* weights, const float* trans,
+                           const float* g_comp_rgb, const float* g_acc, const float* g_depth, int R,
+                           int S, int white_bkgd, int act_mode, float* g_raw_rgb, float* g_raw_sigma,
+                           aon_stream_t stream);
+
+/* aon_adam_step: one torch.optim.Adam step (model.py:386-389: betas (0.9, 0.999), eps 1e-8, no weight
+ * decay) over a FLAT parameter buffer; `step` counts from 1; lr is the value optimizer_step computed
+ * (model.py:402-419); grads are multiplied by grad_scale first (1/world after a sum all-reduce). */
+int aon_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n,
+                  double lr, double beta1, double beta2, double eps, long step, double grad_scale,
+                  aon_stream_t stream);
+
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */
 long aon_launch_count(int reset);

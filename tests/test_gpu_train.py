@@ -1,0 +1,195 @@
+"""GPU: the training-path kernels of csrc/train_ops.cu (stage 1) against the oracle and ITS autograd.
+
+* aon_pos_enc / aon_pos_enc_backward        vs oracle.pos_enc (helper.py:136-140) and torch autograd of it (fp64)
+* aon_composite / aon_composite_backward    vs oracle activations + volumetric_rendering (helper.py:157-195) and torch
+  autograd of them (fp64), both activation modes, both backgrounds, incl. empty and saturated rays and dL/dacc, dL/ddepth
+* aon_adam_step                             vs torch.optim.Adam over several steps
+* end to end: parameter gradients of loss0 + loss1 of a randomized training batch through nerf.NeRF / NeRF_AE_Art
+  (native sampling, pos_enc, compositing + library GEMMs) vs autograd of the oracle on the CPU with the same random draws.
+Tolerances are written at each assert."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_cpu as O
+from tests.test_gpu_parity import _make_net
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b, floor=1e-6):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(floor)).item()
+
+
+def test_pos_enc_forward_backward(built_lib):
+    lib = built_lib
+    torch.manual_seed(0)
+    for L in (10, 4):
+        x = (torch.rand(777, 3) * 8 - 4)
+        want = O.pos_enc(x, 0, L)
+        got = lib.pos_enc(x.to(DEV), L)
+        assert got.shape == want.shape
+        assert (got.cpu() - want).abs().max() < 2e-6           # sinf (CUDA) vs torch.sin (CPU): <= 2 ulp at |sin| <= 1
+        g = torch.randn_like(want)
+        xd = x.double().requires_grad_(True)
+        O.pos_enc(xd, 0, L).backward(g.double())
+        gx = lib.pos_enc_backward(x.to(DEV), g.to(DEV), L)
+        assert _rel(gx, xd.grad) < 1e-5                          # fp32 evaluation of a sum of 2 L terms scaled by 2^k
+
+
+def _raw(R, S, seed, kind):
+    g = torch.Generator().manual_seed(seed)
+    raw_rgb = torch.randn(R, S, 3, generator=g) * 2
+    raw_sigma = torch.randn(R, S, generator=g) * 3
+    if kind == "empty":
+        raw_sigma = raw_sigma - 40.0        # relu -> exactly 0; softplus -> ~1e-18
+    elif kind == "saturated":
+        raw_sigma = raw_sigma.abs() * 50 + 100
+    t = torch.sort(2 + 4 * torch.rand(R, S, generator=g), -1)[0]
+    d = F.normalize(torch.randn(R, 3, generator=g), dim=-1) * (0.5 + torch.rand(R, 1, generator=g))
+    return raw_rgb, raw_sigma, t, d
+
+
+def _oracle_composite(raw_rgb, raw_sigma, t, d, wb, mode):
+    if mode == 0:
+        rgb, sigma = torch.sigmoid(raw_rgb), torch.relu(raw_sigma)
+    else:
+        rgb, sigma = torch.sigmoid(raw_rgb) * (1 + 2 * 0.001) - 0.001, F.softplus(raw_sigma + (-1.0))
+    return O.volumetric_rendering(rgb, sigma[..., None], t, d, wb)   # comp, acc, weights, depth
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("wb", [True, False])
+@pytest.mark.parametrize("kind", ["normal", "empty", "saturated"])
+def test_composite_forward_backward(built_lib, mode, wb, kind):
+    lib = built_lib
+    R, S = 67, 193
+    raw_rgb, raw_sigma, t, d = _raw(R, S, 3 + mode, kind)
+    dev = lambda x: x.to(DEV).contiguous()
+    comp, acc, depth, w, tr = lib.composite(dev(raw_rgb), dev(raw_sigma), dev(t), dev(d), wb, mode)
+    want = _oracle_composite(raw_rgb, raw_sigma, t, d, wb, mode)
+    for got, ref, name in ((comp, want[0], "rgb"), (acc, want[1], "acc"), (w, want[2], "weights"), (depth, want[3], "depth")):
+        assert (got.cpu() - ref).abs().max() < 5e-6 * max(1.0, ref.abs().max().item()), name   # fp32 sum order only
+    # adjoint vs fp64 autograd of the oracle, with gradients on all three outputs
+    g = torch.Generator().manual_seed(11)
+    g_rgb, g_acc, g_depth = torch.randn(R, 3, generator=g), torch.randn(R, generator=g), torch.randn(R, generator=g)
+    rr, rs = raw_rgb.double().requires_grad_(True), raw_sigma.double().requires_grad_(True)
+    c64, a64, _, d64 = _oracle_composite(rr, rs, t.double(), d.double(), wb, mode)
+    ((c64 * g_rgb.double()).sum() + (a64 * g_acc.double()).sum() + (d64 * g_depth.double()).sum()).backward()
+    got_rgb, got_sigma = lib.composite_backward(dev(raw_rgb), dev(raw_sigma), dev(t), dev(d), w, tr, dev(g_rgb), dev(g_acc),
+                                                dev(g_depth), wb, mode)
+    assert torch.isfinite(got_rgb).all() and torch.isfinite(got_sigma).all()
+    # (almost) empty rays: every non-zero gradient sits on samples whose alpha = 1 - exp(-tiny) is a few fp32 ulps of 1.0,
+    # where the fp32 forward itself (the reference's too) carries percent-level error -> absolute bar (upstream g ~ 1)
+    fl = 1e-2 if kind == "empty" else 1e-6
+    assert _rel(got_rgb, rr.grad, floor=fl) < 2e-5
+    assert _rel(got_sigma, rs.grad, floor=1e-12) < 2e-4      # 1 - alpha cancels in fp32 where alpha -> 1
+    # rgb-only gradient (the reference's training loss): NULL dL/dacc, dL/ddepth
+    got_rgb2, got_sigma2 = lib.composite_backward(dev(raw_rgb), dev(raw_sigma), dev(t), dev(d), w, tr, dev(g_rgb), None, None, wb, mode)
+    rr.grad = rs.grad = None
+    c64 = _oracle_composite(rr, rs, t.double(), d.double(), wb, mode)[0]
+    (c64 * g_rgb.double()).sum().backward()
+    assert _rel(got_rgb2, rr.grad, floor=fl) < 2e-5 and _rel(got_sigma2, rs.grad, floor=1e-12) < 2e-4
+
+
+def test_adam_step_matches_torch(built_lib):
+    lib = built_lib
+    torch.manual_seed(1)
+    n = 100003
+    p0 = torch.randn(n, device=DEV)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=5e-4, betas=(0.9, 0.999))
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 8):
+        g = torch.randn(n, device=DEV) * (10.0 ** -(step % 4))
+        lr = 5e-4 * (0.5 + 0.1 * step)
+        for pg in opt.param_groups:
+            pg["lr"] = lr
+        ref.grad = g.clone()
+        opt.step()
+        lib.adam_step(p, g, m, v, lr, 0.9, 0.999, 1e-8, step)
+        assert (p - ref.detach()).abs().max() < 1e-6 * max(1.0, lr / 5e-4)          # a few ulp of the update
+    st = opt.state[ref]
+    assert _rel(m, st["exp_avg"]) < 1e-6 and _rel(v, st["exp_avg_sq"]) < 1e-6
+
+
+def _oracle_grads(sd, kind, rays, target, t_rand, u, dtype):
+    c = lambda x: x.to(dtype)
+    p = {k: c(v).clone().requires_grad_(True) for k, v in sd.items()}
+    lat = O.code_library(p, torch.tensor([0]), torch.tensor([3])) if kind == "autodecoder" else None
+    out = O.nerf_forward(p, {k: c(v) for k, v in rays.items()}, True, True, 2.0, 6.0, latents=lat, t_rand=c(t_rand), u=c(u))
+    loss = O.img2mse(out[0][0], c(target)) + O.img2mse(out[1][0], c(target))
+    loss.backward()
+    return loss.item(), {k: v.grad for k, v in p.items() if v.grad is not None}
+
+
+@pytest.mark.parametrize("sharp", [False, True])
+@pytest.mark.parametrize("kind", ["vanilla", "autodecoder"])
+def test_training_gradients_match_oracle_autograd(built_lib, kind, sharp):
+    """loss0 + loss1 of one randomized batch: d loss / d every parameter through our training path vs autograd of the
+    oracle (CPU) with the same stratified / inverse-CDF random draws.  The bar is tied to the reference's own fp32 noise
+    floor (its distance from an fp64 evaluation): a 1-ulp move of a fine sample is amplified by the 2^9 encoding frequency,
+    so with sharp densities the fp32 reference gradient itself is only reproducible to ~1e-3."""
+    from aon_b200 import nerf
+    torch.manual_seed(0)
+    sd = O.make_state_dict(kind, 0, sharp=sharp)
+    net = _make_net(nerf, kind, sd, torch.device(DEV)).train()
+    rays = {k: v[:96].contiguous() for k, v in O.sapien_rays(10, 12, seed=4).items()}
+    R = rays["rays_o"].shape[0]
+    target = torch.rand(R, 3)
+    t_rand, u = torch.rand(R, 65), torch.rand(R, 128)
+    loss32, g32 = _oracle_grads(sd, kind, rays, target, t_rand, u, torch.float32)
+    loss64, g64 = _oracle_grads(sd, kind, rays, target, t_rand, u, torch.float64)
+    lat_d = None
+    if kind == "autodecoder":
+        lat = O.code_library(sd, torch.tensor([0]), torch.tensor([3]))
+        lat_d = {k: v.detach().to(DEV).requires_grad_(True) for k, v in lat.items()}
+    rd = {k: v.to(DEV) for k, v in rays.items()}
+    args = (rd, True, True, 2.0, 6.0) + ((lat_d,) if lat_d is not None else ())
+    got = net(*args, t_rand=t_rand.to(DEV), u=u.to(DEV))
+    loss = nerf.img2mse(got[0][0], target.to(DEV)) + nerf.img2mse(got[1][0], target.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - loss64) < max(1e-5, 5 * abs(loss32 - loss64))
+    ours, floor, worst = 0.0, 0.0, None
+    grads = {n: prm.grad for n, prm in net.named_parameters()}
+    if lat_d is not None:
+        pre = "code_library.embedding_instance_"
+        for k, full, row in (("density", pre + "shape.weight", 0), ("color", pre + "appearance.weight", 0),
+                             ("articulation", pre + "articulation.weight", 3)):
+            grads[full] = torch.zeros_like(sd[full]).to(DEV)
+            grads[full][row] = lat_d[k].grad[0]
+    assert set(grads) == set(g64)
+    for name, g in grads.items():
+        assert g is not None, name
+        e = _rel(g, g64[name], floor=1e-9)
+        if e > ours:
+            ours, worst = e, name
+        floor = max(floor, _rel(g32[name], g64[name], floor=1e-9))
+    print("kind %s sharp %s: ours vs fp64 %.3e (worst %s), fp32 reference vs fp64 %.3e" % (kind, sharp, ours, worst, floor))
+    assert ours < max(2e-4, 4 * floor), (ours, floor, worst)
+
+
+def test_flat_adam_training_updates_packed_weights(built_lib):
+    """lit.FlatAdam: parameters / grads are views of flat buffers, one aon_adam_step per step, and the kernels' packed-weight
+    cache notices the in-place update (the next eval render changes)."""
+    from types import SimpleNamespace
+    from aon_b200 import lit
+    dev = torch.device(DEV)
+    torch.manual_seed(0)
+    s = lit.build_system(SimpleNamespace(exp_type="vanilla", run_max_steps=100, white_back=True)).to(dev)
+    s.lr_delay_steps = 0
+    rays = {k: v.to(dev) for k, v in O.sapien_rays(8, 8, seed=2).items()}
+    batch = dict(rays, target=torch.rand(64, 3, device=dev))
+    before = s.render_rays(dict(rays))["comp_rgb"].clone()
+    tr = lit.Trainer(max_steps=3)
+    tr.fit(s, ({k: v[None] for k, v in batch.items()} for _ in range(3)))
+    opt = s._optimizer
+    assert isinstance(opt, lit.FlatAdam) and opt.steps == 3
+    n = sum(p.numel() for p in s.parameters())
+    assert opt.flat.numel() == n == 2 * 595844
+    for p in s.parameters():
+        assert opt.flat.data_ptr() <= p.data_ptr() < opt.flat.data_ptr() + 4 * n
+    after = s.render_rays(dict(rays))["comp_rgb"]
+    assert (after - before).abs().max() > 1e-4
