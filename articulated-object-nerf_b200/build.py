@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libaon_b200.so")
-SOURCES = ["aon_api.cu", "render_simt.cu", "render_tc.cu", "train_ops.cu"]
+SOURCES = ["aon_api.cu", "render_simt.cu", "render_tc.cu", "train_ops.cu", "gemm_tc.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 

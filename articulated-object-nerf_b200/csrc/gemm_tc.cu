@@ -1,0 +1,487 @@
+// gemm_tc.cu -- tcgen05 GEMMs of the TRAINING path (stage 2): forward, dgrad and wgrad of the MLP's
+// nn.Linear layers (model.py:99-118) on the 5th-gen tensor cores, fp16 hi+lo split operands (3 MMAs per K step, fp32
+// accumulation in TMEM) like the parity mode of the fused render kernel.
+//
+// Data layout.  Every activation / gradient matrix X[rows, feat] lives in HBM ONCE, as two 16-bit planes (hi, lo) in the
+// "k-group packed" layout  PK(rows, feat) = [rows/128][feat/8][128][8]:  a 128-row x 8-feature slab is 2 KB contiguous.
+//   * as the K-major A operand of forward / dgrad (rows = samples, contraction = features) a (row tile, K chunk) is one
+//     contiguous block that lands in shared memory in the UMMA canonical no-swizzle layout with LBO = 2048, SBO = 128;
+//   * as an MN-major operand of wgrad (dW = dY^T X: contraction = samples) THE SAME bytes are the canonical MN-major
+//     layout ((8,m),(8,k)):((1,SBO),(8,LBO)) with SBO = slab stride, LBO = 128 -- no transposed copy is ever written.
+// Weights are packed per step into PW(rows, contraction) = [contraction/8][rows][8] (K-major B operand), once as W
+// (forward) and once as W^T (dgrad).
+//
+// One CTA = one 128 x N output tile (N <= 256): warp 0 = producer (bulk copies global -> 2-stage shared-memory ring,
+// mbarrier complete_tx), warp 1 = MMA issuer (one elected thread, tcgen05.mma cta_group::1 kind::f16, tcgen05.commit
+// releases ring slots / publishes the accumulator), warps 2-5 = epilogue (tcgen05.ld, bias / ReLU / ReLU-mask, pack to
+// hi+lo, coalesced 16-byte stores).  96 KB of shared memory and <= 256 TMEM columns per CTA -> two CTAs per SM, so one
+// CTA's epilogue overlaps the other's MMAs.  wgrad CTAs loop over their share of the sample tiles (split-K) and write fp32
+// partial tiles that wgrad_reduce_kernel sums in a fixed order (deterministic).
+#include "aon_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace aon {
+using namespace ptx;
+
+constexpr int GT_THREADS = 192;
+constexpr int GT_KC = 32;                       // contraction elements per pipeline stage
+constexpr int GT_NS = 2;                        // stages
+constexpr uint32_t GT_A_PLANE = 128 * GT_KC * 2;   // 8 KB: 128 rows x 32 k x 2 B
+constexpr uint32_t GT_B_PLANE = 256 * GT_KC * 2;   // 16 KB: up to 256 rows
+constexpr uint32_t GT_STAGE = 2 * GT_A_PLANE + 2 * GT_B_PLANE;   // 48 KB
+constexpr uint32_t GT_SMEM = GT_NS * GT_STAGE + 1024;             // + alignment slack
+
+struct GtParams {
+  AonGemm g;
+};
+
+__device__ __forceinline__ void gt_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  return (uint32_t)__half_as_ushort(__float2half_rn(a)) | ((uint32_t)__half_as_ushort(__float2half_rn(b)) << 16);
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P) {
+  extern __shared__ unsigned char gt_smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar[2 * GT_NS + 1];
+  __shared__ uint32_t s_tmem;
+  const AonGemm& g = P.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sm0 = (smem_u32(gt_smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (GT_NS + s); };
+  const uint32_t accum = bar0 + 8u * (2 * GT_NS);
+  const int N = g.N;
+  const uint32_t tmem_cols = N <= 32 ? 32u : (N <= 64 ? 64u : (N <= 128 ? 128u : 256u));
+  const bool x3 = g.x3 != 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < GT_NS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(smem_u32(&s_tmem), tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  // ---- work decomposition -----------------------------------------------------------------------------------------
+  // NT: blockIdx.x = row tile; stages = for each segment, K chunks of GT_KC.
+  // TN: blockIdx.x = 128-feature tile of operand A (output rows), blockIdx.y = split; stages = row tiles x 4 quarter tiles.
+  const bool tn = g.mode == AON_GEMM_TN;
+  int t_begin = 0, t_end = 0;
+  if (tn) {
+    t_begin = (int)blockIdx.y * g.tiles_per_split;
+    t_end = min(g.m_tiles, t_begin + g.tiles_per_split);
+  }
+  long n_stage_total = 0;
+  if (tn) n_stage_total = (long)max(0, t_end - t_begin) * (128 / GT_KC);
+  else for (int sgi = 0; sgi < g.nseg; ++sgi) n_stage_total += (g.kext[sgi] + GT_KC - 1) / GT_KC;
+
+  if (warp == 0) {
+    // ================= producer =================
+    long it = 0;
+    if (!tn) {
+      const long tile = blockIdx.x;
+      for (int sgi = 0; sgi < g.nseg; ++sgi) {
+        const char* a_pl[2] = {(const char*)g.a_hi[sgi], (const char*)g.a_lo[sgi]};
+        const char* b_pl[2] = {(const char*)g.b_hi[sgi], (const char*)g.b_lo[sgi]};
+        const long a_tile = tile * (long)(g.a_feat[sgi] / 8) * 2048;
+        for (int k0 = 0; k0 < g.kext[sgi]; k0 += GT_KC, ++it) {
+          const int s = (int)(it % GT_NS);
+          const int kc = min(GT_KC, g.kext[sgi] - k0), nkg = kc / 8;
+          gt_wait(empty(s), (uint32_t)(((it / GT_NS) & 1) ^ 1));
+          const uint32_t a_bytes = (uint32_t)nkg * 2048u, b_piece = (uint32_t)N * 16u;
+          const int planes = x3 ? 2 : 1;
+          if (lane == 0) mbar_arrive_expect_tx(full(s), (uint32_t)planes * (a_bytes + (uint32_t)nkg * b_piece));
+          __syncwarp();
+          const uint32_t st = sm0 + (uint32_t)s * GT_STAGE;
+          // pieces: per plane 1 A block + nkg B row blocks
+          const int per_plane = 1 + nkg;
+          for (int p = lane; p < planes * per_plane; p += 32) {
+            const int pl = p / per_plane, q = p % per_plane;
+            if (q == 0) {
+              bulk_g2s(st + (uint32_t)pl * GT_A_PLANE, a_pl[pl] + a_tile + (long)((g.a_off[sgi] + k0) / 8) * 2048, a_bytes, full(s));
+            } else {
+              const int kg = q - 1;
+              bulk_g2s(st + 2 * GT_A_PLANE + (uint32_t)pl * GT_B_PLANE + (uint32_t)kg * b_piece,
+                       b_pl[pl] + ((long)((g.b_off[sgi] + k0) / 8 + kg) * g.b_feat[sgi] + g.b_row0[sgi]) * 16, b_piece, full(s));
+            }
+          }
+        }
+      }
+    } else {
+      const char* a_pl[2] = {(const char*)g.a_hi[0], (const char*)g.a_lo[0]};
+      const char* b_pl[2] = {(const char*)g.b_hi[0], (const char*)g.b_lo[0]};
+      const int a_ng0 = g.a_off[0] / 8 + (int)blockIdx.x * 16, b_ng0 = g.b_off[0] / 8, b_ngn = N / 8;
+      const int planes = x3 ? 2 : 1, per_plane = 16 + b_ngn;
+      constexpr uint32_t PIECE = GT_KC * 16;     // 32 rows x 16 B
+      for (int t = t_begin; t < t_end; ++t) {
+        for (int q4 = 0; q4 < 128 / GT_KC; ++q4, ++it) {
+          const int s = (int)(it % GT_NS);
+          gt_wait(empty(s), (uint32_t)(((it / GT_NS) & 1) ^ 1));
+          if (lane == 0) mbar_arrive_expect_tx(full(s), (uint32_t)(planes * per_plane) * PIECE);
+          __syncwarp();
+          const uint32_t st = sm0 + (uint32_t)s * GT_STAGE;
+          for (int p = lane; p < planes * per_plane; p += 32) {
+            const int pl = p / per_plane, q = p % per_plane;
+            if (q < 16) {
+              bulk_g2s(st + (uint32_t)pl * GT_A_PLANE + (uint32_t)q * PIECE,
+                       a_pl[pl] + (((long)t * (g.a_feat[0] / 8) + a_ng0 + q) * 128 + q4 * GT_KC) * 16, PIECE, full(s));
+            } else {
+              const int ng = q - 16;
+              bulk_g2s(st + 2 * GT_A_PLANE + (uint32_t)pl * GT_B_PLANE + (uint32_t)ng * PIECE,
+                       b_pl[pl] + (((long)t * (g.b_feat[0] / 8) + b_ng0 + ng) * 128 + q4 * GT_KC) * 16, PIECE, full(s));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_f16(128, N, 0) | (tn ? ((1u << 15) | (1u << 16)) : 0u);
+      uint32_t accumulate = 0;
+      long it = 0;
+      auto issue_stage = [&](int s, int kc) {
+        const uint32_t st = sm0 + (uint32_t)s * GT_STAGE;
+        const uint32_t a_hi = st, a_lo = st + GT_A_PLANE, b_hi = st + 2 * GT_A_PLANE, b_lo = b_hi + GT_B_PLANE;
+        for (int kk = 0; kk < kc / 16; ++kk) {
+          uint32_t a_off, b_off, a_lbo, a_sbo, b_lbo, b_sbo;
+          if (!tn) {   // K-major: [kg][rows][8]
+            a_off = (uint32_t)kk * 4096u; a_lbo = 2048u; a_sbo = 128u;
+            b_off = (uint32_t)kk * 2u * (uint32_t)N * 16u; b_lbo = (uint32_t)N * 16u; b_sbo = 128u;
+          } else {     // MN-major: [ng][GT_KC rows][8]: MN-group stride (SBO) = GT_KC*16, K-group stride (LBO) = 128
+            a_off = (uint32_t)kk * 256u; a_lbo = 128u; a_sbo = GT_KC * 16u;
+            b_off = a_off; b_lbo = 128u; b_sbo = GT_KC * 16u;
+          }
+          mma_f16_ss(tmem_base, smem_desc(a_hi + a_off, a_lbo, a_sbo), smem_desc(b_hi + b_off, b_lbo, b_sbo), idesc, accumulate);
+          accumulate = 1;
+          if (x3) {
+            mma_f16_ss(tmem_base, smem_desc(a_lo + a_off, a_lbo, a_sbo), smem_desc(b_hi + b_off, b_lbo, b_sbo), idesc, 1);
+            mma_f16_ss(tmem_base, smem_desc(a_hi + a_off, a_lbo, a_sbo), smem_desc(b_lo + b_off, b_lbo, b_sbo), idesc, 1);
+          }
+        }
+      };
+      if (!tn) {
+        for (int sgi = 0; sgi < g.nseg; ++sgi)
+          for (int k0 = 0; k0 < g.kext[sgi]; k0 += GT_KC, ++it) {
+            const int s = (int)(it % GT_NS);
+            gt_wait(full(s), (uint32_t)((it / GT_NS) & 1));
+            tc_fence_after();
+            issue_stage(s, min(GT_KC, g.kext[sgi] - k0));
+            mma_commit(empty(s));
+          }
+      } else {
+        for (; it < n_stage_total; ++it) {
+          const int s = (int)(it % GT_NS);
+          gt_wait(full(s), (uint32_t)((it / GT_NS) & 1));
+          tc_fence_after();
+          issue_stage(s, GT_KC);
+          mma_commit(empty(s));
+        }
+      }
+      mma_commit(accum);
+    }
+  } else {
+    // ================= epilogue (warps 2..5: TMEM lane quadrant = warp % 4) =================
+    const int quad = warp & 3, row = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    if (n_stage_total > 0) {
+      gt_wait(accum, 0);
+      tc_fence_after();
+    }
+    const long tile = blockIdx.x;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t r[32];
+      const int nc = min(32, N - c0);          // 16 or 32
+      if (n_stage_total > 0) {
+        tmem_ld32(lane_base + (uint32_t)c0, r);  // N = 16: the upper 16 columns are allocated (32 columns) but unused
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * g.inv_scale;
+      if (g.epi == AON_GEMM_EPI_PARTIAL) {
+        float* dst = g.partial + (((long)blockIdx.y * gridDim.x + blockIdx.x) * 128 + row) * N + c0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          if (i < nc) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        continue;
+      }
+      if (g.epi == AON_GEMM_EPI_LINEAR) {
+        if (g.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < nc) v[i] += __ldg(g.bias + c0 + i);
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+      } else {   // AON_GEMM_EPI_MASK: pass where the forward activation (hi plane of PK(rows, mask_feat)) is > 0
+        if (g.mask_hi) {
+          const char* mp = (const char*)g.mask_hi + ((tile * (g.mask_feat / 8) + (g.mask_off + c0) / 8) * 128 + row) * 16;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q * 8 < nc) {
+              const uint4 m = *reinterpret_cast<const uint4*>(mp + (long)q * 2048);
+              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t lo16 = w[j] & 0xffffu, hi16 = w[j] >> 16;
+                if (!((lo16 & 0x7fffu) != 0 && (lo16 & 0x8000u) == 0)) v[q * 8 + 2 * j] = 0.f;
+                if (!((hi16 & 0x7fffu) != 0 && (hi16 & 0x8000u) == 0)) v[q * 8 + 2 * j + 1] = 0.f;
+              }
+            }
+          }
+        }
+      }
+      if (g.out_f32) {
+        float* dst = g.out_f32 + (tile * 128 + row) * g.ldc;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (c0 + i < g.n_valid) dst[c0 + i] = v[i];
+      }
+      if (g.out_hi) {
+        const long base = ((tile * (g.out_feat / 8) + (g.out_off + c0) / 8) * 128 + row) * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q * 8 < nc) {
+            float s[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = v[q * 8 + j] * g.out_scale;
+            uint4 h;
+            h.x = pack_h2(s[0], s[1]); h.y = pack_h2(s[2], s[3]); h.z = pack_h2(s[4], s[5]); h.w = pack_h2(s[6], s[7]);
+            *reinterpret_cast<uint4*>((char*)g.out_hi + base + (long)q * 2048) = h;
+            if (g.out_lo) {
+              const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+              float l[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                l[2 * j] = s[2 * j] - __half2float(__ushort_as_half((unsigned short)(hw[j] & 0xffffu)));
+                l[2 * j + 1] = s[2 * j + 1] - __half2float(__ushort_as_half((unsigned short)(hw[j] >> 16)));
+              }
+              uint4 lo;
+              lo.x = pack_h2(l[0], l[1]); lo.y = pack_h2(l[2], l[3]); lo.z = pack_h2(l[4], l[5]); lo.w = pack_h2(l[6], l[7]);
+              *reinterpret_cast<uint4*>((char*)g.out_lo + base + (long)q * 2048) = lo;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// ---- packing ------------------------------------------------------------------------------------------------------------
+// fp32 [rows_in, C] (row stride ld; source row of packed row m is m / row_div) -> PK(m_tiles*128, c_pad) hi (+ lo) * scale;
+// rows >= M and columns >= C are zero.
+__global__ void pack_rows_kernel(const float* __restrict__ src, long ld, int C, long M, int row_div, int m_tiles, int c_pad,
+                                 float scale, uint4* __restrict__ hi, uint4* __restrict__ lo) {
+  const long total = (long)m_tiles * (c_pad / 8) * 128;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int row = (int)(idx & 127);
+    const long rest = idx >> 7;
+    const int kg = (int)(rest % (c_pad / 8));
+    const long tile = rest / (c_pad / 8);
+    const long m = tile * 128 + row;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = kg * 8 + j;
+      s[j] = (m < M && c < C) ? src[(m / row_div) * ld + c] * scale : 0.f;
+    }
+    uint4 h;
+    h.x = pack_h2(s[0], s[1]); h.y = pack_h2(s[2], s[3]); h.z = pack_h2(s[4], s[5]); h.w = pack_h2(s[6], s[7]);
+    hi[idx] = h;
+    if (lo) {
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+      float l[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        l[2 * j] = s[2 * j] - __half2float(__ushort_as_half((unsigned short)(hw[j] & 0xffffu)));
+        l[2 * j + 1] = s[2 * j + 1] - __half2float(__ushort_as_half((unsigned short)(hw[j] >> 16)));
+      }
+      uint4 q;
+      q.x = pack_h2(l[0], l[1]); q.y = pack_h2(l[2], l[3]); q.z = pack_h2(l[4], l[5]); q.w = pack_h2(l[6], l[7]);
+      lo[idx] = q;
+    }
+  }
+}
+
+// nn.Linear weight W [out, in] fp32 -> PW(r_pad, k_pad) = [k_pad/8][r_pad][8] hi (+ lo) * scale;
+// transpose = 0: rows = out features, contraction = in features (forward); 1: rows = in, contraction = out (dgrad).
+__global__ void pack_linear_kernel(const float* __restrict__ W, int out_f, int in_f, int transpose, int r_pad, int k_pad, float scale,
+                                   uint4* __restrict__ hi, uint4* __restrict__ lo) {
+  const int total = (k_pad / 8) * r_pad;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx % r_pad, kg = idx / r_pad;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kg * 8 + j;
+      const int o = transpose ? k : r, i = transpose ? r : k;
+      s[j] = (o < out_f && i < in_f) ? W[(long)o * in_f + i] * scale : 0.f;
+    }
+    uint4 h;
+    h.x = pack_h2(s[0], s[1]); h.y = pack_h2(s[2], s[3]); h.z = pack_h2(s[4], s[5]); h.w = pack_h2(s[6], s[7]);
+    hi[idx] = h;
+    if (lo) {
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+      float l[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        l[2 * j] = s[2 * j] - __half2float(__ushort_as_half((unsigned short)(hw[j] & 0xffffu)));
+        l[2 * j + 1] = s[2 * j + 1] - __half2float(__ushort_as_half((unsigned short)(hw[j] >> 16)));
+      }
+      uint4 q;
+      q.x = pack_h2(l[0], l[1]); q.y = pack_h2(l[2], l[3]); q.z = pack_h2(l[4], l[5]); q.w = pack_h2(l[6], l[7]);
+      lo[idx] = q;
+    }
+  }
+}
+
+// dst[r, col_off + c] (or dst[c, col_off + r] if transpose) = scale * sum_split partial[split][r][c], fixed summation order.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int rows_pad, int N, float scale,
+                                    float* __restrict__ dst, long ld, int col_off, int rows_valid, int cols_valid, int transpose) {
+  const int total = rows_pad * N;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / N, c = idx % N;
+    if (r >= rows_valid || c >= cols_valid) continue;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(long)k * total + idx];
+    if (transpose) dst[(long)c * ld + col_off + r] = s * scale;
+    else dst[(long)r * ld + col_off + c] = s * scale;
+  }
+}
+
+// Column sums of a PK(rows, feat) tensor (hi + lo planes): partial[split][feat] = sum over the split's row tiles.
+__global__ void __launch_bounds__(128) colsum_packed_kernel(const uint4* __restrict__ hi, const uint4* __restrict__ lo, int feat,
+                                                             int m_tiles, int tiles_per_split, float* __restrict__ partial) {
+  __shared__ float red[4][8];
+  const int kg = blockIdx.x, split = blockIdx.y, row = threadIdx.x;
+  const int t0 = split * tiles_per_split, t1 = min(m_tiles, t0 + tiles_per_split);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int t = t0; t < t1; ++t) {
+    const long idx = ((long)t * (feat / 8) + kg) * 128 + row;
+    const uint4 h = hi[idx];
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s[2 * j] += __half2float(__ushort_as_half((unsigned short)(hw[j] & 0xffffu)));
+      s[2 * j + 1] += __half2float(__ushort_as_half((unsigned short)(hw[j] >> 16)));
+    }
+    if (lo) {
+      const uint4 l = lo[idx];
+      const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[2 * j] += __half2float(__ushort_as_half((unsigned short)(lw[j] & 0xffffu)));
+        s[2 * j + 1] += __half2float(__ushort_as_half((unsigned short)(lw[j] >> 16)));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    for (int o = 16; o > 0; o >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+  if ((row & 31) == 0)
+    for (int j = 0; j < 8; ++j) red[row >> 5][j] = s[j];
+  __syncthreads();
+  if (row < 8) partial[(long)split * feat + kg * 8 + row] = (red[0][row] + red[1][row]) + (red[2][row] + red[3][row]);
+}
+
+}  // namespace aon
+
+using namespace aon;
+
+extern "C" int aon_gemm_tc(const AonGemm* gp, aon_stream_t stream) {
+  AON_REQUIRE(gp != nullptr, "aon_gemm_tc: null descriptor");
+  const AonGemm& g = *gp;
+  AON_REQUIRE(g.mode == AON_GEMM_NT || g.mode == AON_GEMM_TN, "aon_gemm_tc: bad mode %d", g.mode);
+  AON_REQUIRE(g.N >= 16 && g.N <= 256 && g.N % 16 == 0, "aon_gemm_tc: N = %d must be a multiple of 16 in [16, 256]", g.N);
+  AON_REQUIRE(g.m_tiles >= 0, "aon_gemm_tc: bad m_tiles");
+  AON_REQUIRE(g.nseg >= 1 && g.nseg <= AON_GEMM_MAX_SEG, "aon_gemm_tc: bad nseg %d", g.nseg);
+  for (int s = 0; s < g.nseg; ++s) {
+    AON_REQUIRE(g.a_hi[s] && g.b_hi[s] && (!g.x3 || (g.a_lo[s] && g.b_lo[s])), "aon_gemm_tc: null operand plane (segment %d)", s);
+    AON_REQUIRE(g.a_feat[s] % 8 == 0 && g.b_feat[s] % 8 == 0 && g.a_off[s] % 8 == 0 && g.b_off[s] % 8 == 0,
+                "aon_gemm_tc: feature counts / offsets must be multiples of 8 (segment %d)", s);
+    if (g.mode == AON_GEMM_NT) AON_REQUIRE(g.kext[s] > 0 && g.kext[s] % 16 == 0, "aon_gemm_tc: kext must be a positive multiple of 16");
+  }
+  if (g.m_tiles == 0) return AON_OK;
+  int dev = 0, major = 0;
+  AON_CUDA_CHECK(cudaGetDevice(&dev));
+  AON_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("aon_gemm_tc needs an sm_100 device (found compute capability %d.x)", major);
+    return AON_E_UNSUPPORTED;
+  }
+  dim3 grid;
+  if (g.mode == AON_GEMM_NT) {
+    AON_REQUIRE(g.epi == AON_GEMM_EPI_LINEAR || g.epi == AON_GEMM_EPI_MASK, "aon_gemm_tc: NT mode takes a LINEAR or MASK epilogue");
+    grid = dim3((unsigned)g.m_tiles);
+  } else {
+    AON_REQUIRE(g.epi == AON_GEMM_EPI_PARTIAL && g.partial != nullptr && g.nseg == 1, "aon_gemm_tc: TN mode writes partial tiles");
+    AON_REQUIRE(g.a_tiles >= 1 && g.splits >= 1 && g.tiles_per_split >= 1 && (long)g.splits * g.tiles_per_split >= g.m_tiles,
+                "aon_gemm_tc: bad TN decomposition");
+    grid = dim3((unsigned)g.a_tiles, (unsigned)g.splits);
+  }
+  AON_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
+  GtParams P;
+  P.g = g;
+  gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM, (cudaStream_t)stream>>>(P);
+  AON_LAUNCH_CHECK();
+  return AON_OK;
+}
+
+extern "C" int aon_pack_rows(const float* src, long ld, int C, long M, int row_div, int m_tiles, int c_pad, float scale, void* hi,
+                             void* lo, aon_stream_t stream) {
+  AON_REQUIRE(src && hi, "aon_pack_rows: null pointer");
+  AON_REQUIRE(C >= 1 && c_pad % 8 == 0 && c_pad >= C && row_div >= 1 && m_tiles >= 0 && M <= (long)m_tiles * 128,
+              "aon_pack_rows: bad sizes C=%d c_pad=%d M=%ld m_tiles=%d", C, c_pad, M, m_tiles);
+  if (m_tiles == 0) return AON_OK;
+  const long total = (long)m_tiles * (c_pad / 8) * 128;
+  const long blocks = (total + 255) / 256;
+  pack_rows_kernel<<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, (cudaStream_t)stream>>>(src, ld, C, M, row_div, m_tiles, c_pad, scale,
+                                                                                                   (uint4*)hi, (uint4*)lo);
+  AON_LAUNCH_CHECK();
+  return AON_OK;
+}
+
+extern "C" int aon_pack_linear(const float* W, int out_features, int in_features, int transpose, int r_pad, int k_pad, float scale,
+                               void* hi, void* lo, aon_stream_t stream) {
+  AON_REQUIRE(W && hi, "aon_pack_linear: null pointer");
+  const int rows = transpose ? in_features : out_features, kk = transpose ? out_features : in_features;
+  AON_REQUIRE(r_pad >= rows && k_pad >= kk && k_pad % 8 == 0 && r_pad % 8 == 0, "aon_pack_linear: bad padding r_pad=%d k_pad=%d", r_pad, k_pad);
+  const int total = (k_pad / 8) * r_pad;
+  pack_linear_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, out_features, in_features, transpose, r_pad, k_pad, scale,
+                                                                            (uint4*)hi, (uint4*)lo);
+  AON_LAUNCH_CHECK();
+  return AON_OK;
+}
+
+extern "C" int aon_wgrad_reduce(const float* partial, int splits, int rows_pad, int N, float scale, float* dst, long ld, int col_off,
+                                int rows_valid, int cols_valid, int transpose, aon_stream_t stream) {
+  AON_REQUIRE(partial && dst && splits >= 1 && rows_pad >= 1 && N >= 1, "aon_wgrad_reduce: bad arguments");
+  const int total = rows_pad * N;
+  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partial, splits, rows_pad, N, scale, dst, ld, col_off,
+                                                                             rows_valid, cols_valid, transpose);
+  AON_LAUNCH_CHECK();
+  return AON_OK;
+}
+
+extern "C" int aon_colsum_packed(const void* hi, const void* lo, int feat, int m_tiles, int splits, float* partial, aon_stream_t stream) {
+  AON_REQUIRE(hi && partial && feat % 8 == 0 && feat >= 8 && splits >= 1 && m_tiles >= 0, "aon_colsum_packed: bad arguments");
+  const int tps = (m_tiles + splits - 1) / splits;
+  colsum_packed_kernel<<<dim3(feat / 8, splits), 128, 0, (cudaStream_t)stream>>>((const uint4*)hi, (const uint4*)lo, feat, m_tiles,
+                                                                                 tps > 0 ? tps : 1, partial);
+  AON_LAUNCH_CHECK();
+  return AON_OK;
+}

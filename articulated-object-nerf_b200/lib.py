@@ -41,6 +41,11 @@ SYMBOLS = {
     "aon_composite": (_i, [_fp, _fp, _fp, _l, _fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _vp]),
     "aon_composite_backward": (_i, [_fp, _fp, _fp, _l, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),
     "aon_adam_step": (_i, [_fp, _fp, _fp, _fp, _l, _d, _d, _d, _d, _l, _d, _vp]),
+    "aon_gemm_tc": (_i, [_vp, _vp]),
+    "aon_pack_rows": (_i, [_fp, _l, _i, _l, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "aon_pack_linear": (_i, [_fp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "aon_wgrad_reduce": (_i, [_fp, _i, _i, _i, _f, _fp, _l, _i, _i, _i, _i, _vp]),
+    "aon_colsum_packed": (_i, [_vp, _vp, _i, _i, _i, _fp, _vp]),
     "aon_launch_count": (_l, [_i]),
 }
 
@@ -275,6 +280,146 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, 
         _check(lib.aon_adam_step(_ptr(params, "params"), _ptr(grads, "grads"), _ptr(exp_avg, "exp_avg"),
                                  _ptr(exp_avg_sq, "exp_avg_sq"), params.numel(), float(lr), float(beta1), float(beta2),
                                  float(eps), int(step), float(grad_scale), _stream()), "aon_adam_step")
+
+
+# ---- training path, stage 2: tcgen05 GEMMs on packed 16-bit hi/lo planes (csrc/gemm_tc.cu) ---------------------
+GEMM_NT, GEMM_TN = 0, 1
+EPI_LINEAR, EPI_MASK, EPI_PARTIAL = 0, 1, 2
+_SEG = 2
+
+
+class AonGemm(C.Structure):
+    """Mirror of `struct AonGemm` in include/aon.h."""
+    _fields_ = [("mode", _i), ("epi", _i), ("x3", _i), ("nseg", _i), ("N", _i), ("m_tiles", _i),
+                ("a_hi", _vp * _SEG), ("a_lo", _vp * _SEG), ("b_hi", _vp * _SEG), ("b_lo", _vp * _SEG),
+                ("a_feat", _i * _SEG), ("a_off", _i * _SEG), ("kext", _i * _SEG),
+                ("b_feat", _i * _SEG), ("b_off", _i * _SEG), ("b_row0", _i * _SEG),
+                ("a_tiles", _i), ("splits", _i), ("tiles_per_split", _i), ("relu", _i),
+                ("partial", _vp), ("inv_scale", _f), ("out_scale", _f),
+                ("n_valid", _i), ("mask_feat", _i), ("mask_off", _i), ("out_feat", _i), ("out_off", _i), ("reserved", _i),
+                ("bias", _vp), ("mask_hi", _vp), ("out_f32", _vp), ("ldc", _l), ("out_hi", _vp), ("out_lo", _vp)]
+
+
+class PK:
+    """Activation / gradient matrix [m_tiles*128, feat] as 16-bit hi (+ lo) planes in the k-group packed layout
+    [rows/128][feat/8][128][8] (see csrc/gemm_tc.cu)."""
+    __slots__ = ("hi", "lo", "m_tiles", "feat")
+
+    def __init__(self, m_tiles: int, feat: int, device, x3: bool = True):
+        assert feat % 8 == 0
+        self.m_tiles, self.feat = m_tiles, feat
+        self.hi = torch.empty(m_tiles * feat * 128, dtype=torch.float16, device=device)
+        self.lo = torch.empty_like(self.hi) if x3 else None
+
+    def to_dense(self) -> torch.Tensor:
+        """fp32 [rows, feat] (hi + lo), for tests."""
+        v = self.hi.float() + (self.lo.float() if self.lo is not None else 0)
+        return v.view(self.m_tiles, self.feat // 8, 128, 8).permute(0, 2, 1, 3).reshape(self.m_tiles * 128, self.feat)
+
+
+class PW:
+    """Packed weight [k_pad/8][r_pad][8] hi (+ lo) planes: r_pad GEMM output rows, k_pad contraction."""
+    __slots__ = ("hi", "lo", "r_pad", "k_pad")
+
+    def __init__(self, r_pad: int, k_pad: int, device, x3: bool = True):
+        self.r_pad, self.k_pad = r_pad, k_pad
+        self.hi = torch.empty(r_pad * k_pad, dtype=torch.float16, device=device)
+        self.lo = torch.empty_like(self.hi) if x3 else None
+
+
+def _p(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def pack_rows(src: torch.Tensor, M: int, m_tiles: int, c_pad: int, scale: float, row_div: int = 1, x3: bool = True) -> PK:
+    """src fp32 [rows_in, C] (last dim contiguous) -> PK(m_tiles*128, c_pad) * scale; packed row m reads src[m // row_div]."""
+    lib = load()
+    if not (src.is_cuda and src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1):
+        raise AonError("pack_rows: src must be a CUDA float32 [rows, C] tensor with contiguous rows")
+    out = PK(m_tiles, c_pad, src.device, x3)
+    with torch.cuda.device(src.device):
+        _check(lib.aon_pack_rows(src.data_ptr(), src.stride(0), src.shape[1], M, row_div, m_tiles, c_pad, float(scale),
+                                 out.hi.data_ptr(), _p(out.lo), _stream()), "aon_pack_rows")
+    return out
+
+
+def pack_linear(W: torch.Tensor, transpose: bool, r_pad: int, k_pad: int, scale: float, x3: bool = True) -> PW:
+    lib = load()
+    out = PW(r_pad, k_pad, W.device, x3)
+    with torch.cuda.device(W.device):
+        _check(lib.aon_pack_linear(_ptr(W, "W"), W.shape[0], W.shape[1], int(transpose), r_pad, k_pad, float(scale),
+                                   out.hi.data_ptr(), _p(out.lo), _stream()), "aon_pack_linear")
+    return out
+
+
+def gemm_nt(segs, N: int, m_tiles: int, device, *, epi: int = EPI_LINEAR, bias=None, relu: bool = False, mask=None,
+            inv_scale: float = 1.0, out_f32: Optional[torch.Tensor] = None, n_valid: int = 0, out: Optional[PK] = None,
+            out_off: int = 0, out_scale: float = 1.0, x3: bool = True) -> None:
+    """segs: [(A: PK, a_off, kext, B: PW, b_off, b_row0)], all accumulating into D[rows, N]."""
+    lib = load()
+    g = AonGemm()
+    g.mode, g.epi, g.x3, g.nseg, g.N, g.m_tiles = GEMM_NT, epi, int(x3), len(segs), N, m_tiles
+    for i, (A, a_off, kext, B, b_off, b_row0) in enumerate(segs):
+        if A.m_tiles != m_tiles or a_off + kext > A.feat or b_off + kext > B.k_pad or b_row0 + N > B.r_pad:
+            raise AonError("gemm_nt: segment %d out of range" % i)
+        g.a_hi[i], g.a_lo[i], g.b_hi[i], g.b_lo[i] = A.hi.data_ptr(), _p(A.lo), B.hi.data_ptr(), _p(B.lo)
+        g.a_feat[i], g.a_off[i], g.kext[i] = A.feat, a_off, kext
+        g.b_feat[i], g.b_off[i], g.b_row0[i] = B.r_pad, b_off, b_row0
+    g.relu, g.inv_scale, g.out_scale = int(relu), inv_scale, out_scale
+    g.bias = _p(bias)
+    if mask is not None:
+        mk, moff = mask
+        g.mask_hi, g.mask_feat, g.mask_off = mk.hi.data_ptr(), mk.feat, moff
+    if out_f32 is not None:
+        if out_f32.shape[0] < m_tiles * 128 or out_f32.stride(1) != 1:
+            raise AonError("gemm_nt: out_f32 must hold m_tiles*128 rows")
+        g.out_f32, g.ldc, g.n_valid = out_f32.data_ptr(), out_f32.stride(0), n_valid or N
+    if out is not None:
+        if out.m_tiles != m_tiles or out_off + N > out.feat:
+            raise AonError("gemm_nt: packed output out of range")
+        g.out_hi, g.out_lo, g.out_feat, g.out_off = out.hi.data_ptr(), _p(out.lo), out.feat, out_off
+    with torch.cuda.device(device):
+        _check(lib.aon_gemm_tc(C.byref(g), _stream()), "aon_gemm_tc(NT)")
+
+
+def gemm_tn(A: PK, a_off: int, a_tiles: int, B: PK, b_off: int, N: int, splits: int, x3: bool = True) -> torch.Tensor:
+    """partial[split][a_tiles*128][N] = sum over the split's rows of A[:, a_off + 128 t + i] * B[:, b_off + j]."""
+    lib = load()
+    if A.m_tiles != B.m_tiles or a_off + a_tiles * 128 > A.feat or b_off + N > B.feat:
+        raise AonError("gemm_tn: operands out of range")
+    splits = max(1, min(splits, A.m_tiles))
+    tps = (A.m_tiles + splits - 1) // splits
+    splits = (A.m_tiles + tps - 1) // tps
+    part = torch.empty(splits, a_tiles * 128, N, dtype=torch.float32, device=A.hi.device)
+    g = AonGemm()
+    g.mode, g.epi, g.x3, g.nseg, g.N, g.m_tiles = GEMM_TN, EPI_PARTIAL, int(x3), 1, N, A.m_tiles
+    g.a_hi[0], g.a_lo[0], g.b_hi[0], g.b_lo[0] = A.hi.data_ptr(), _p(A.lo), B.hi.data_ptr(), _p(B.lo)
+    g.a_feat[0], g.a_off[0], g.b_feat[0], g.b_off[0] = A.feat, a_off, B.feat, b_off
+    g.a_tiles, g.splits, g.tiles_per_split = a_tiles, splits, tps
+    g.partial, g.inv_scale = part.data_ptr(), 1.0
+    with torch.cuda.device(A.hi.device):
+        _check(lib.aon_gemm_tc(C.byref(g), _stream()), "aon_gemm_tc(TN)")
+    return part
+
+
+def wgrad_reduce(partial: torch.Tensor, scale: float, dst: torch.Tensor, col_off: int, rows_valid: int, cols_valid: int,
+                 transpose: bool = False) -> None:
+    lib = load()
+    splits, rows_pad, N = partial.shape
+    with torch.cuda.device(dst.device):
+        _check(lib.aon_wgrad_reduce(partial.data_ptr(), splits, rows_pad, N, float(scale), _ptr(dst, "dst"), dst.stride(0), col_off,
+                                    rows_valid, cols_valid, int(transpose), _stream()), "aon_wgrad_reduce")
+
+
+def colsum_packed(x: PK, splits: int = 16) -> torch.Tensor:
+    """[splits, feat] partial column sums (hi + lo) of a PK tensor."""
+    lib = load()
+    splits = max(1, min(splits, x.m_tiles))
+    part = torch.empty(splits, x.feat, dtype=torch.float32, device=x.hi.device)
+    with torch.cuda.device(x.hi.device):
+        _check(lib.aon_colsum_packed(x.hi.data_ptr(), _p(x.lo), x.feat, x.m_tiles, splits, part.data_ptr(), _stream()),
+               "aon_colsum_packed")
+    return part
 
 
 # ---- debug hooks (exported by the library but deliberately not part of include/aon.h) ------------------

@@ -163,6 +163,62 @@ int aon_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   double lr, double beta1, double beta2, double eps, long step, double grad_scale,
                   aon_stream_t stream);
 
+/* ---- training path, stage 2: tcgen05 GEMMs for the MLP's forward / dgrad / wgrad (csrc/gemm_tc.cu) ------------
+ * Replaces the nn.Linear contractions of NeRFMLP.forward (model.py:99-118) and their autograd adjoints in
+ * training_step (model.py:256-282).  Operands are 16-bit hi (+ lo) planes in two packed layouts:
+ *   PK(rows, feat) = [rows/128][feat/8][128][8]   activations / gradients (rows = samples)
+ *   PW(rows, k)    = [k/8][rows][8]               weights (rows = output rows of the GEMM, k = contraction)
+ * AON_GEMM_NT:  D[128-row tile, N] = sum_seg A_seg[tile, a_off:+kext] . B_seg[b_row0:+N, b_off:+kext]^T   (forward, dgrad)
+ *               A = PK tensors, B = PW tensors; up to AON_GEMM_MAX_SEG segments accumulate into one tile
+ *               (skip / view concatenations, the two consumers of the last trunk activation).
+ * AON_GEMM_TN:  D[128-feature tile of A, N] = sum_rows A[rows, a_off + 128 tile:+128]^T . B[rows, b_off:+N]    (wgrad)
+ *               A, B = PK tensors read as MN-major operands; grid = (a_tiles, splits); every CTA writes an fp32 partial
+ *               tile to partial[split][a_tiles*128][N]; aon_wgrad_reduce sums the splits in a fixed order.
+ * Epilogues (NT): LINEAR  v = acc*inv_scale + bias, optional ReLU;   MASK  v = acc*inv_scale where the hi plane of the
+ * forward activation mask_hi = PK(rows, mask_feat) is > 0 else 0 (ReLU adjoint).  v is written as fp32 row-major
+ * out_f32[row, 0:n_valid] (row stride ldc) and/or as PK(rows, out_feat) planes at feature offset out_off, times out_scale. */
+#define AON_GEMM_MAX_SEG 2
+#define AON_GEMM_NT 0
+#define AON_GEMM_TN 1
+#define AON_GEMM_EPI_LINEAR 0
+#define AON_GEMM_EPI_MASK 1
+#define AON_GEMM_EPI_PARTIAL 2
+typedef struct AonGemm {
+  int mode, epi, x3, nseg;     /* x3: 1 = hi+lo operands, 3 MMAs per K step (fp32-grade); 0 = hi planes only */
+  int N, m_tiles;              /* output columns (multiple of 16, <= 256); number of 128-row tiles of the PK tensors */
+  const void* a_hi[AON_GEMM_MAX_SEG];
+  const void* a_lo[AON_GEMM_MAX_SEG];
+  const void* b_hi[AON_GEMM_MAX_SEG];
+  const void* b_lo[AON_GEMM_MAX_SEG];
+  int a_feat[AON_GEMM_MAX_SEG], a_off[AON_GEMM_MAX_SEG], kext[AON_GEMM_MAX_SEG];
+  int b_feat[AON_GEMM_MAX_SEG], b_off[AON_GEMM_MAX_SEG], b_row0[AON_GEMM_MAX_SEG];
+  int a_tiles, splits, tiles_per_split, relu;
+  float* partial;
+  float inv_scale, out_scale;
+  int n_valid, mask_feat, mask_off, out_feat, out_off, reserved;
+  const float* bias;
+  const void* mask_hi;
+  float* out_f32;
+  long ldc;
+  void* out_hi;
+  void* out_lo;
+} AonGemm;
+int aon_gemm_tc(const AonGemm* gemm, aon_stream_t stream);
+/* fp32 [*, C] rows (row stride ld; packed row m reads source row m / row_div -- per-ray inputs broadcast to their
+ * samples) -> PK(m_tiles*128, c_pad) hi (+ lo if non-NULL) times scale; rows >= M and columns >= C are zero. */
+int aon_pack_rows(const float* src, long ld, int C, long M, int row_div, int m_tiles, int c_pad, float scale,
+                  void* hi, void* lo, aon_stream_t stream);
+/* nn.Linear weight [out, in] fp32 -> PW(r_pad, k_pad) hi (+ lo) times scale; transpose 0: rows = out, k = in
+ * (forward); 1: rows = in, k = out (dgrad). */
+int aon_pack_linear(const float* W, int out_features, int in_features, int transpose, int r_pad, int k_pad,
+                    float scale, void* hi, void* lo, aon_stream_t stream);
+/* dst[r, col_off + c] (transpose: dst[c, col_off + r]) = scale * sum_split partial[split][r][c], r < rows_valid, c < cols_valid */
+int aon_wgrad_reduce(const float* partial, int splits, int rows_pad, int N, float scale, float* dst, long ld,
+                     int col_off, int rows_valid, int cols_valid, int transpose, aon_stream_t stream);
+/* column sums of a PK(m_tiles*128, feat) tensor (bias gradients): partial[split][feat], split = contiguous tile ranges */
+int aon_colsum_packed(const void* hi, const void* lo, int feat, int m_tiles, int splits, float* partial,
+                      aon_stream_t stream);
+
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */
 long aon_launch_count(int reset);
