@@ -8,10 +8,11 @@ Same class names, constructor defaults, ``forward`` signatures, return structure
 * ``CodeLibraryArticulated``        <- models/code_library.py:12-71
 
 ``forward`` under ``torch.no_grad()`` (validation / ``--run_eval``) runs entirely in the fused CUDA
-kernels.  When gradients are required (``training_step``) the sampling stages still run in the
-kernels (they are detached in the reference too, helper.py:249) and the MLP + compositing of the
-sampled points runs through torch autograd on the GPU -- the native backward is SURVEY.md 8(f) F1.
-There is no CPU path: every call needs CUDA tensors and the built library.
+kernels.  When gradients are required (``training_step``) the level is evaluated stage by stage so that it can be
+differentiated: sampling, positional encoding and activations + compositing run in our kernels with
+hand-written adjoints (csrc/train_ops.cu); the vanilla MLP's contractions -- forward, dgrad and wgrad -- run as tcgen05
+GEMMs (csrc/gemm_tc.cu via train_tc.py; ``train_gemm = "torch"`` selects library GEMMs under autograd instead, which is
+also what the auto-decoder MLP still uses).  There is no CPU path: every call needs CUDA tensors and the built library.
 """
 from __future__ import annotations
 
@@ -27,6 +28,7 @@ import torch.nn.functional as F
 import torch.nn.init as init
 
 from . import lib as L
+from . import train_tc
 
 Tensor = torch.Tensor
 
@@ -246,6 +248,8 @@ class _LevelLoop(nn.Module):
     def _init_cache(self):
         self._cache = {"coarse": _PackCache(), "fine": _PackCache()}
         self.precision = default_precision()
+        # training_step contractions: "tc" = hand-written tcgen05 GEMMs (train_tc.py; vanilla MLP), "torch" = library GEMMs
+        self.train_gemm = os.environ.get("AON_TRAIN_GEMM", "tc")
 
     def _render(self, rays, randomized, white_bkgd, near, far, latents=None, t_rand=None, u=None):
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
@@ -290,7 +294,9 @@ class _LevelLoop(nn.Module):
                 t_vals = L.sample_pdf(t_vals, weights.detach().contiguous(), self.num_fine_samples,
                                       u=None if u is None else u.contiguous())
             samples = o[:, None, :] + t_vals[..., None] * d[:, None, :]
-            if latents is None:
+            if latents is None and self.train_gemm == "tc":
+                raw_rgb, raw_sigma = train_tc.vanilla_mlp(pos_enc_cuda(samples, 0, 10), view_enc, samples.shape[1], mlp)
+            elif latents is None:
                 raw_rgb, raw_sigma = mlp(pos_enc_cuda(samples, 0, 10), view_enc)
             else:
                 raw_rgb, raw_sigma = mlp(samples, view_enc, latents)

@@ -1,0 +1,163 @@
+"""Training-path MLP on the tcgen05 GEMMs of csrc/gemm_tc.cu (stage 2).
+
+``vanilla_mlp(enc, view_enc, S, mlp)`` evaluates NeRFMLP.forward (models/vanilla_nerf/model.py:95-120) for training:
+every nn.Linear runs as an ``aon_gemm_tc`` launch on packed fp16 hi+lo planes (3 MMAs per K step, fp32 accumulation:
+fp32-grade results), and the backward -- written by hand, no autograd inside -- runs the dgrad chain with the ReLU mask
+in the GEMM epilogue, the weight gradients as split-K tcgen05 GEMMs that read the saved activation / gradient planes as
+MN-major operands, and the bias gradients as packed column sums.
+
+Scaling (exact powers of two, so nothing is lost): activations x8, weights x64 (the fused render kernel's choice, which
+keeps the lo planes out of the fp16 subnormal range) and gradients x SG with SG = 2^floor(log2(rays)) -- the loss
+gradient is O(1 / rays) (mean over 3 * rays residuals), so scaled gradients stay O(1).
+"""
+from __future__ import annotations
+
+import math
+from typing import List
+
+import torch
+
+from . import lib as L
+
+SA, SW = 8.0, 64.0
+
+
+def _pad(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def _pad_bias(b: torch.Tensor, n: int) -> torch.Tensor:
+    if b.numel() == n:
+        return b.detach().contiguous()
+    out = torch.zeros(n, dtype=torch.float32, device=b.device)
+    out[: b.numel()] = b.detach()
+    return out
+
+
+def _wgrad(dY: L.PK, out_valid: int, X: L.PK, x_off: int, n_cols: int, cols_valid: int, dst: torch.Tensor, col_off: int,
+           inv: float) -> None:
+    """dst[0:out_valid, col_off : col_off + cols_valid] = inv * dY^T X[:, x_off : x_off + n_cols]."""
+    a_tiles = dY.feat // 128
+    part = L.gemm_tn(dY, 0, a_tiles, X, x_off, n_cols, max(1, 296 // a_tiles))
+    L.wgrad_reduce(part, inv, dst, col_off, out_valid, cols_valid)
+
+
+def _wgrad_head(X: L.PK, in_valid: int, G: L.PK, out_valid: int, dst: torch.Tensor, inv: float) -> None:
+    """Heads (1 / 3 output features, padded to 16): dst[o, i] = inv * sum_m G[m, o] X[m, i] as the transposed product
+    (rows = the 128-feature tiles of X, columns = the 16 padded outputs)."""
+    a_tiles = X.feat // 128
+    part = L.gemm_tn(X, 0, a_tiles, G, 0, 16, max(1, 296 // a_tiles))
+    L.wgrad_reduce(part, inv, dst, 0, in_valid, out_valid, transpose=True)
+
+
+class _VanillaMLPFn(torch.autograd.Function):
+    """(enc [M,63], view_enc [R,27], S, w0, b0, ..., w11, b11) -> raw [M,4] = (rgb, sigma); parameters in
+    NeRFMLP.linears() order: pts_linears.0-7, views_linear.0, bottleneck_layer, density_layer, rgb_layer."""
+
+    @staticmethod
+    def forward(ctx, enc, view_enc, S, *params):
+        M, dev = enc.shape[0], enc.device
+        tiles = (M + 127) // 128
+        W = [p.detach().contiguous() for p in params[0::2]]
+        B = [p.detach() for p in params[1::2]]
+        E = L.pack_rows(enc.detach(), M, tiles, 64, SA)
+        V = L.pack_rows(view_enc.detach(), M, tiles, 32, SA, row_div=S)
+        inv = 1.0 / (SA * SW)
+        h: List[L.PK] = []
+        x, kx = E, 64
+        for i in range(8):
+            Wp = L.pack_linear(W[i], False, 256, _pad(W[i].shape[1], 16) if i != 5 else 320, SW)
+            segs = [(x, 0, kx, Wp, 0, 0)]
+            if i == 5:
+                segs.append((E, 0, 64, Wp, 256, 0))
+            out = L.PK(tiles, 256, dev)
+            L.gemm_nt(segs, 256, tiles, dev, bias=B[i].contiguous(), relu=True, inv_scale=inv, out=out, out_scale=SA)
+            h.append(out)
+            x, kx = out, 256
+        raw = torch.empty(tiles * 128, 4, dtype=torch.float32, device=dev)
+        Wd = L.pack_linear(W[10], False, 16, 256, SW)
+        L.gemm_nt([(h[7], 0, 256, Wd, 0, 0)], 16, tiles, dev, bias=_pad_bias(B[10], 16), inv_scale=inv, out_f32=raw[:, 3:], n_valid=1)
+        Wb = L.pack_linear(W[9], False, 256, 256, SW)
+        bott = L.PK(tiles, 256, dev)
+        L.gemm_nt([(h[7], 0, 256, Wb, 0, 0)], 256, tiles, dev, bias=B[9].contiguous(), inv_scale=inv, out=bott, out_scale=SA)
+        Wv = L.pack_linear(W[8], False, 128, 288, SW)
+        hv = L.PK(tiles, 128, dev)
+        L.gemm_nt([(bott, 0, 256, Wv, 0, 0), (V, 0, 32, Wv, 256, 0)], 128, tiles, dev, bias=B[8].contiguous(), relu=True,
+                  inv_scale=inv, out=hv, out_scale=SA)
+        Wr = L.pack_linear(W[11], False, 16, 128, SW)
+        L.gemm_nt([(hv, 0, 128, Wr, 0, 0)], 16, tiles, dev, bias=_pad_bias(B[11], 16), inv_scale=inv, out_f32=raw, n_valid=3)
+        ctx.pk = (E, V, h, bott, hv)
+        ctx.W = W
+        ctx.dims = (M, tiles, S)
+        return raw[:M]
+
+    @staticmethod
+    def backward(ctx, g_raw):
+        E, V, h, bott, hv = ctx.pk
+        W = ctx.W
+        M, tiles, S = ctx.dims
+        dev = g_raw.device
+        R = max(1, M // S)
+        SG = float(2 ** int(math.floor(math.log2(R))))
+        g_raw = g_raw.contiguous()
+        Gr = L.pack_rows(g_raw, M, tiles, 16, SG)                       # columns 0-2 (+ sigma in column 3, unused here: zero weight rows)
+        Gs = L.pack_rows(g_raw[:, 3:], M, tiles, 16, SG)                 # sigma gradient alone (C = 1)
+        inv_w = 1.0 / (SG * SA)
+        gW = [torch.zeros_like(w) for w in W]
+        gB = [None] * 12
+        gB[11] = g_raw[:, :3].sum(0)
+        gB[10] = g_raw[:, 3:].sum(0)
+
+        def colsum(G: L.PK, n: int) -> torch.Tensor:
+            return L.colsum_packed(G, 16).sum(0)[:n] / SG
+
+        # rgb_layer: the packed gradient has 4 live columns (r, g, b, sigma); W_r^T padded with zero rows ignores sigma
+        _wgrad_head(hv, 128, Gr, 3, gW[11], inv_w)
+        WrT = L.pack_linear(W[11], True, 128, 16, SW)
+        d_hv = L.PK(tiles, 128, dev)
+        L.gemm_nt([(Gr, 0, 16, WrT, 0, 0)], 128, tiles, dev, epi=L.EPI_MASK, mask=(hv, 0), inv_scale=1.0 / SW, out=d_hv)
+        # views_linear.0 : inputs [bottleneck(256), view enc(27)]
+        _wgrad(d_hv, 128, bott, 0, 256, 256, gW[8], 0, inv_w)
+        _wgrad(d_hv, 128, V, 0, 32, 27, gW[8], 256, inv_w)
+        gB[8] = colsum(d_hv, 128)
+        WvT = L.pack_linear(W[8], True, 288, 128, SW)
+        d_bott = L.PK(tiles, 256, dev)
+        L.gemm_nt([(d_hv, 0, 128, WvT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / SW, out=d_bott)
+        # bottleneck_layer and density_layer both read the last trunk activation h[7]
+        _wgrad(d_bott, 256, h[7], 0, 256, 256, gW[9], 0, inv_w)
+        gB[9] = colsum(d_bott, 256)
+        _wgrad_head(h[7], 256, Gs, 1, gW[10], inv_w)
+        WbT = L.pack_linear(W[9], True, 256, 256, SW)
+        WdT = L.pack_linear(W[10], True, 256, 16, SW)
+        d = L.PK(tiles, 256, dev)
+        L.gemm_nt([(d_bott, 0, 256, WbT, 0, 0), (Gs, 0, 16, WdT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[7], 0),
+                  inv_scale=1.0 / SW, out=d)
+        # trunk, last layer first: pts_linears.i maps x_i -> h[i], x_0 = E, x_i = h[i-1] (+ E for i = 5)
+        for i in range(7, -1, -1):
+            x = E if i == 0 else h[i - 1]
+            kin = 64 if i == 0 else 256
+            _wgrad(d, 256, x, 0, kin, 63 if i == 0 else 256, gW[i], 0, inv_w)
+            if i == 5:
+                _wgrad(d, 256, E, 0, 64, 63, gW[5], 256, inv_w)
+            gB[i] = colsum(d, 256)
+            if i == 0:
+                break
+            WT = L.pack_linear(W[i], True, 320 if i == 5 else 256, 256, SW)
+            nd = L.PK(tiles, 256, dev)
+            L.gemm_nt([(d, 0, 256, WT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[i - 1], 0), inv_scale=1.0 / SW, out=nd)
+            d = nd
+        ctx.pk = None
+        out = [None, None, None]
+        for w, b in zip(gW, gB):
+            out += [w, b]
+        return tuple(out)
+
+
+def vanilla_mlp(enc: torch.Tensor, view_enc: torch.Tensor, S: int, mlp) -> tuple:
+    """enc [R,S,63] / [M,63], view_enc [R,27] -> (raw_rgb [R,S,3], raw_sigma [R,S,1]) through the tcgen05 GEMMs."""
+    params = []
+    for lin in mlp.linears():
+        params += [lin.weight, lin.bias]
+    raw = _VanillaMLPFn.apply(enc.reshape(-1, enc.shape[-1]).contiguous(), view_enc.contiguous(), S, *params)
+    R = raw.shape[0] // S
+    return raw[:, :3].reshape(R, S, 3), raw[:, 3:].reshape(R, S, 1)

@@ -193,3 +193,30 @@ def test_flat_adam_training_updates_packed_weights(built_lib):
         assert opt.flat.data_ptr() <= p.data_ptr() < opt.flat.data_ptr() + 4 * n
     after = s.render_rays(dict(rays))["comp_rgb"]
     assert (after - before).abs().max() > 1e-4
+
+
+def test_vanilla_mlp_tc_matches_autograd(built_lib):
+    """train_tc.vanilla_mlp (tcgen05 forward / dgrad / wgrad GEMMs, hi+lo fp16 operands) against fp64 torch autograd of
+    NeRFMLP.forward (model.py:95-120) on the same inputs: outputs and every parameter gradient to fp32 grade."""
+    from aon_b200 import nerf, train_tc
+    torch.manual_seed(0)
+    dev = torch.device(DEV)
+    R, S = 37, 65                                             # M = 2405: ragged last row tile
+    mlp = nerf.NeRFMLP(0, 10, 4).to(dev)
+    with torch.no_grad():
+        for p in mlp.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.3, 0.3)
+    enc = torch.randn(R, S, 63, device=dev).clamp(-3, 3)
+    view = torch.randn(R, 27, device=dev).clamp(-1, 1)
+    g = torch.randn(R, S, 4, device=dev) / (3 * R)
+    raw_rgb, raw_sigma = train_tc.vanilla_mlp(enc, view, S, mlp)
+    ((raw_rgb * g[..., :3]).sum() + (raw_sigma * g[..., 3:]).sum()).backward()
+    got = {n: p.grad.clone() for n, p in mlp.named_parameters()}
+    ref = nerf.NeRFMLP(0, 10, 4).double()
+    ref.load_state_dict({k: v.double().cpu() for k, v in mlp.state_dict().items()})
+    rr, rs = ref(enc.double().cpu(), view.double().cpu())
+    ((rr * g[..., :3].double().cpu()).sum() + (rs * g[..., 3:].double().cpu()).sum()).backward()
+    assert _rel(raw_rgb, rr) < 1e-5 and _rel(raw_sigma, rs) < 1e-5
+    for n, p in ref.named_parameters():
+        assert _rel(got[n], p.grad, floor=1e-12) < 2e-5, n
