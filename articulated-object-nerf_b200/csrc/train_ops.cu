@@ -83,7 +83,8 @@ __global__ void composite_fwd_kernel(const float* __restrict__ raw_rgb, const fl
   const float* rs = raw_sigma + (size_t)ray * S;
   float trans = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cdepth = 0.f, cacc = 0.f;
   float t_cur = tv[0];
-  for (int s = 0; s < S; ++s) {
+#pragma unroll 4
+  for (int s = 0; s < S; ++s) {   // only `trans` is carried from sample to sample: unrolled so the loads and exps overlap
     const float t_next = (s + 1 < S) ? tv[s + 1] : 0.f;
     const float r = act_rgb(rr[3 * s + 0], act_mode), g = act_rgb(rr[3 * s + 1], act_mode), b = act_rgb(rr[3 * s + 2], act_mode);
     const float sigma = act_sigma(rs[s], act_mode);
@@ -136,6 +137,7 @@ __global__ void composite_bwd_kernel(const float* __restrict__ raw_rgb, const fl
   const float ga = g_acc ? g_acc[ray] : 0.f, gd = g_depth ? g_depth[ray] : 0.f;
   const float gbg = white_bkgd ? (gr + gg + gb) : 0.f;
   float B = 0.f;
+#pragma unroll 4
   for (int s = S - 1; s >= 0; --s) {
     const float t_cur = tv[s];
     const float raw_r = rr[3 * s + 0], raw_g = rr[3 * s + 1], raw_b = rr[3 * s + 2], raw_s = rs[s];

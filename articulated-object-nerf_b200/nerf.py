@@ -298,6 +298,8 @@ class _LevelLoop(nn.Module):
                 raw_rgb, raw_sigma = train_tc.vanilla_mlp(pos_enc_cuda(samples, 0, 10), view_enc, samples.shape[1], mlp)
             elif latents is None:
                 raw_rgb, raw_sigma = mlp(pos_enc_cuda(samples, 0, 10), view_enc)
+            elif self.train_gemm == "tc":
+                raw_rgb, raw_sigma = train_tc.autodecoder_mlp(samples.contiguous(), view_enc, latents, mlp)
             else:
                 raw_rgb, raw_sigma = mlp(samples, view_enc, latents)
             comp, acc, weights, depth = composite_cuda(raw_rgb, raw_sigma, t_vals, d, white_bkgd, 0 if latents is None else 1)

@@ -103,7 +103,7 @@ class _VanillaMLPFn(torch.autograd.Function):
         Gr = L.pack_rows(g_raw, M, tiles, 16, SG)                       # columns 0-2 (+ sigma in column 3, unused here: zero weight rows)
         Gs = L.pack_rows(g_raw[:, 3:], M, tiles, 16, SG)                 # sigma gradient alone (C = 1)
         inv_w = 1.0 / (SG * SA)
-        gW = [torch.zeros_like(w) for w in W]
+        gW = [torch.empty_like(w) for w in W]           # every entry is written by a wgrad_reduce launch
         gB = [None] * 12
         gB[11] = g_raw[:, :3].sum(0)
         gB[10] = g_raw[:, 3:].sum(0)
@@ -151,6 +151,170 @@ class _VanillaMLPFn(torch.autograd.Function):
         for w, b in zip(gW, gB):
             out += [w, b]
         return tuple(out)
+
+
+def _fold(b: torch.Tensor, W: torch.Tensor, parts) -> torch.Tensor:
+    """bias + sum W[:, c0:c0+len(code)] @ code: the latent columns of a layer contracted once per call (the reference
+    broadcasts the codes to every sample and concatenates, model_autodecoder.py:186-198,226-228)."""
+    out = b.detach().clone()
+    for c0, code in parts:
+        out += W[:, c0:c0 + code.numel()] @ code.reshape(-1)
+    return out.contiguous()
+
+
+class _AutoDecoderMLPFn(torch.autograd.Function):
+    """(pos [M,3], view_enc [R,27], S, shape [1,128], appearance [1,128], articulation [1,32], w0, b0, ...) -> raw [M,4];
+    parameters in NeRFMLP_AE.linears() order: deformations_linear.0-3 (0-3), deformation_layer (4), pts_linears.0-7 (5-12),
+    views_linear.0-3 (13-16), bottleneck_layer (17), density_layer (18), rgb_layer (19).  model_autodecoder.py:171-239."""
+
+    @staticmethod
+    def forward(ctx, pos, view_enc, S, shape, app, art, *params):
+        M, dev = pos.shape[0], pos.device
+        tiles = (M + 127) // 128
+        W = [p.detach().contiguous() for p in params[0::2]]
+        B = [p.detach() for p in params[1::2]]
+        s_, c_, a_ = shape.detach().reshape(-1), app.detach().reshape(-1), art.detach().reshape(-1)
+        inv = 1.0 / (SA * SW)
+        pos = pos.detach().contiguous()
+
+        def lin(segs, w, k_pad, n, bias, relu):
+            Wp = L.pack_linear(w, False, n, k_pad, SW)
+            out = L.PK(tiles, n, dev)
+            L.gemm_nt([(x, 0, k, Wp, off, 0) for x, k, off in segs], n, tiles, dev, bias=bias, relu=relu, inv_scale=inv, out=out,
+                      out_scale=SA)
+            return out
+
+        def head(x, k, w, bias, n_valid):
+            Wp = L.pack_linear(w, False, 16, k, SW)
+            o = torch.empty(tiles * 128, n_valid, dtype=torch.float32, device=dev)
+            L.gemm_nt([(x, 0, k, Wp, 0, 0)], 16, tiles, dev, bias=_pad_bias(bias, 16), inv_scale=inv, out_f32=o, n_valid=n_valid)
+            return o
+
+        # articulation warp: deformation MLP on [pos, shape, articulation]
+        P = L.pack_rows(pos, M, tiles, 16, SA)
+        hd = [lin([(P, 16, 0)], W[0], 176, 128, _fold(B[0], W[0], [(3, s_), (131, a_)]), True)]
+        for i in (1, 2, 3):
+            hd.append(lin([(hd[-1], 128, 0)], W[i], 128, 128, B[i].contiguous(), True))
+        delta = head(hd[3], 128, W[4], B[4], 3)
+        warped = (delta[:M] + pos).contiguous()                                     # model_autodecoder.py:203
+        E = L.pack_rows(L.pos_enc(warped, 10), M, tiles, 64, SA)
+        V = L.pack_rows(view_enc.detach(), M, tiles, 32, SA, row_div=S)
+        h = [lin([(E, 64, 0)], W[5], 192, 256, _fold(B[5], W[5], [(63, s_)]), True)]
+        for i in range(1, 8):
+            if i == 5:
+                h.append(lin([(h[-1], 256, 0), (E, 64, 256)], W[10], 448, 256, _fold(B[10], W[10], [(319, s_)]), True))
+            else:
+                h.append(lin([(h[-1], 256, 0)], W[5 + i], 256, 256, B[5 + i].contiguous(), True))
+        raw = torch.empty(tiles * 128, 4, dtype=torch.float32, device=dev)
+        Wd = L.pack_linear(W[18], False, 16, 256, SW)
+        L.gemm_nt([(h[7], 0, 256, Wd, 0, 0)], 16, tiles, dev, bias=_pad_bias(B[18], 16), inv_scale=inv, out_f32=raw[:, 3:], n_valid=1)
+        bott = lin([(h[7], 256, 0)], W[17], 256, 256, B[17].contiguous(), False)
+        hv = [lin([(bott, 256, 0), (V, 32, 256)], W[13], 416, 128, _fold(B[13], W[13], [(283, c_)]), True)]
+        for i in (1, 2, 3):
+            hv.append(lin([(hv[-1], 128, 0)], W[13 + i], 128, 128, B[13 + i].contiguous(), True))
+        Wr = L.pack_linear(W[19], False, 16, 128, SW)
+        L.gemm_nt([(hv[3], 0, 128, Wr, 0, 0)], 16, tiles, dev, bias=_pad_bias(B[19], 16), inv_scale=inv, out_f32=raw, n_valid=3)
+        ctx.pk = (P, hd, warped, E, V, h, bott, hv)
+        ctx.W, ctx.codes, ctx.dims = W, (s_, c_, a_), (M, tiles, S)
+        return raw[:M]
+
+    @staticmethod
+    def backward(ctx, g_raw):
+        P, hd, warped, E, V, h, bott, hv = ctx.pk
+        W, (s_, c_, a_), (M, tiles, S) = ctx.W, ctx.codes, ctx.dims
+        dev = g_raw.device
+        SG = float(2 ** int(math.floor(math.log2(max(1, M // S)))))
+        inv_w = 1.0 / (SG * SA)
+        g_raw = g_raw.contiguous()
+        gW = [torch.empty_like(w) for w in W]
+        gB = [None] * 20
+        g_s, g_c, g_a = torch.zeros_like(s_), torch.zeros_like(c_), torch.zeros_like(a_)
+
+        def colsum(G, n):
+            return L.colsum_packed(G, 16).sum(0)[:n] / SG
+
+        def dgrad(segs, n, mask, rows_pad, k_pad):
+            """segs: [(dY, kext, weight index, first row of W^T)] -> PK(tiles, n) masked by `mask`."""
+            out = L.PK(tiles, n, dev)
+            gs = [(dY, 0, k, L.pack_linear(W[wi], True, rows_pad[j], k_pad[j], SW), 0, r0) for j, (dY, k, wi, r0) in enumerate(segs)]
+            L.gemm_nt(gs, n, tiles, dev, epi=L.EPI_MASK, mask=None if mask is None else (mask, 0), inv_scale=1.0 / SW, out=out)
+            return out
+
+        def latent(wi, gb, parts):
+            """latent columns of layer wi: dW = gb (x) code, d code = W[:, cols]^T gb."""
+            for c0, code, acc in parts:
+                n = code.numel()
+                gW[wi][:, c0:c0 + n] = torch.outer(gb, code)
+                acc += W[wi][:, c0:c0 + n].t() @ gb
+
+        # ---- colour branch ----
+        Gr = L.pack_rows(g_raw, M, tiles, 16, SG)
+        Gs = L.pack_rows(g_raw[:, 3:], M, tiles, 16, SG)
+        gB[19], gB[18] = g_raw[:, :3].sum(0), g_raw[:, 3:].sum(0)
+        _wgrad_head(hv[3], 128, Gr, 3, gW[19], inv_w)
+        d = dgrad([(Gr, 16, 19, 0)], 128, hv[3], [128], [16])
+        for i in (3, 2, 1):
+            _wgrad(d, 128, hv[i - 1], 0, 128, 128, gW[13 + i], 0, inv_w)
+            gB[13 + i] = colsum(d, 128)
+            d = dgrad([(d, 128, 13 + i, 0)], 128, hv[i - 1], [128], [128])
+        _wgrad(d, 128, bott, 0, 256, 256, gW[13], 0, inv_w)
+        _wgrad(d, 128, V, 0, 32, 27, gW[13], 256, inv_w)
+        gB[13] = colsum(d, 128)
+        latent(13, gB[13], [(283, c_, g_c)])
+        d_bott = dgrad([(d, 128, 13, 0)], 256, None, [416], [128])
+        # ---- trunk ----
+        _wgrad(d_bott, 256, h[7], 0, 256, 256, gW[17], 0, inv_w)
+        gB[17] = colsum(d_bott, 256)
+        _wgrad_head(h[7], 256, Gs, 1, gW[18], inv_w)
+        d = dgrad([(d_bott, 256, 17, 0), (Gs, 16, 18, 0)], 256, h[7], [256, 256], [256, 16])
+        d5 = None
+        for i in range(7, -1, -1):
+            wi = 5 + i
+            x = E if i == 0 else h[i - 1]
+            _wgrad(d, 256, x, 0, 64 if i == 0 else 256, 63 if i == 0 else 256, gW[wi], 0, inv_w)
+            gB[wi] = colsum(d, 256)
+            if i == 5:
+                _wgrad(d, 256, E, 0, 64, 63, gW[wi], 256, inv_w)
+                latent(wi, gB[wi], [(319, s_, g_s)])
+                d5 = d
+            if i == 0:
+                latent(wi, gB[wi], [(63, s_, g_s)])
+                break
+            d = dgrad([(d, 256, wi, 0)], 256, h[i - 1], [448 if i == 5 else 256], [256])
+        # ---- encoding -> warped position -> deformation MLP ----
+        g_enc = torch.empty(tiles * 128, 63, dtype=torch.float32, device=dev)
+        W0T, W5T = L.pack_linear(W[5], True, 192, 256, SW), L.pack_linear(W[10], True, 448, 256, SW)
+        L.gemm_nt([(d, 0, 256, W0T, 0, 0), (d5, 0, 256, W5T, 0, 256)], 64, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / (SW * SG),
+                  out_f32=g_enc, n_valid=63)
+        g_warped = L.pos_enc_backward(warped, g_enc[:M], 10)                        # [M,3]; d warped / d delta = 1
+        Gd = L.pack_rows(g_warped, M, tiles, 16, SG)
+        gB[4] = g_warped.sum(0)
+        _wgrad_head(hd[3], 128, Gd, 3, gW[4], inv_w)
+        d = dgrad([(Gd, 16, 4, 0)], 128, hd[3], [128], [16])
+        for i in (3, 2, 1):
+            _wgrad(d, 128, hd[i - 1], 0, 128, 128, gW[i], 0, inv_w)
+            gB[i] = colsum(d, 128)
+            d = dgrad([(d, 128, i, 0)], 128, hd[i - 1], [128], [128])
+        _wgrad(d, 128, P, 0, 16, 3, gW[0], 0, inv_w)
+        gB[0] = colsum(d, 128)
+        latent(0, gB[0], [(3, s_, g_s), (131, a_, g_a)])
+        ctx.pk = None
+        out = [None, None, None, g_s.view(1, -1), g_c.view(1, -1), g_a.view(1, -1)]
+        for w, b in zip(gW, gB):
+            out += [w, b]
+        return tuple(out)
+
+
+def autodecoder_mlp(pos: torch.Tensor, view_enc: torch.Tensor, latents: dict, mlp) -> tuple:
+    """pos [R,S,3] raw sample positions, view_enc [R,27], latents {density, color, articulation} -> (raw_rgb [R,S,3],
+    raw_sigma [R,S,1]) through the tcgen05 GEMMs; gradients flow to the parameters and the three codes."""
+    R, S, _ = pos.shape
+    params = []
+    for lin in mlp.linears():
+        params += [lin.weight, lin.bias]
+    raw = _AutoDecoderMLPFn.apply(pos.reshape(-1, 3), view_enc.contiguous(), S, latents["density"], latents["color"],
+                                  latents["articulation"], *params)
+    return raw[:, :3].reshape(R, S, 3), raw[:, 3:].reshape(R, S, 1)
 
 
 def vanilla_mlp(enc: torch.Tensor, view_enc: torch.Tensor, S: int, mlp) -> tuple:
