@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
   extern __shared__ unsigned char gt_smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[2 * GT_NS + 1];
   __shared__ uint32_t s_tmem;
+  __shared__ float s_colsum[4][256];     // per epilogue warp: column sums of its 32 rows (bias gradients)
   const AonGemm& g = P.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sm0 = (smem_u32(gt_smem_raw) + 1023u) & ~1023u;
@@ -243,6 +244,24 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
           }
         }
       }
+      if (g.colsum) {
+        // 32 columns x 32 lanes -> lane l holds the sum of column c0 + l over this warp's rows: a transpose-reduce butterfly,
+        // 31 shuffles (each step halves the columns a lane carries and doubles the rows they cover)
+        float t[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t[i] = (i < nc) ? v[i] : 0.f;
+#pragma unroll
+        for (int k = 16; k >= 1; k >>= 1) {
+          const bool up = (lane & k) != 0;
+#pragma unroll
+          for (int i = 0; i < k; ++i) {
+            const float send = up ? t[i] : t[i + k];
+            const float keep = up ? t[i + k] : t[i];
+            t[i] = keep + __shfl_xor_sync(0xffffffffu, send, k);
+          }
+        }
+        s_colsum[quad][c0 + lane] = t[0];
+      }
       if (g.out_f32) {
         float* dst = g.out_f32 + (tile * 128 + row) * g.ldc;
 #pragma unroll
@@ -274,6 +293,12 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
           }
         }
       }
+    }
+    if (g.colsum) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps
+      const int e = tid - 64;                             // 0..127
+      for (int c = e; c < N; c += 128)
+        g.colsum[tile * N + c] = (s_colsum[0][c] + s_colsum[1][c]) + (s_colsum[2][c] + s_colsum[3][c]);
     }
   }
   tc_fence_before();
@@ -426,6 +451,7 @@ extern "C" int aon_gemm_tc(const AonGemm* gp, aon_stream_t stream) {
   dim3 grid;
   if (g.mode == AON_GEMM_NT) {
     AON_REQUIRE(g.epi == AON_GEMM_EPI_LINEAR || g.epi == AON_GEMM_EPI_MASK, "aon_gemm_tc: NT mode takes a LINEAR or MASK epilogue");
+    AON_REQUIRE(g.colsum == nullptr || g.N % 32 == 0, "aon_gemm_tc: colsum needs N to be a multiple of 32");
     grid = dim3((unsigned)g.m_tiles);
   } else {
     AON_REQUIRE(g.epi == AON_GEMM_EPI_PARTIAL && g.partial != nullptr && g.nseg == 1, "aon_gemm_tc: TN mode writes partial tiles");

@@ -297,7 +297,7 @@ class AonGemm(C.Structure):
                 ("a_tiles", _i), ("splits", _i), ("tiles_per_split", _i), ("relu", _i),
                 ("partial", _vp), ("inv_scale", _f), ("out_scale", _f),
                 ("n_valid", _i), ("mask_feat", _i), ("mask_off", _i), ("out_feat", _i), ("out_off", _i), ("reserved", _i),
-                ("bias", _vp), ("mask_hi", _vp), ("out_f32", _vp), ("ldc", _l), ("out_hi", _vp), ("out_lo", _vp)]
+                ("bias", _vp), ("mask_hi", _vp), ("out_f32", _vp), ("ldc", _l), ("out_hi", _vp), ("out_lo", _vp), ("colsum", _vp)]
 
 
 class PK:
@@ -354,8 +354,9 @@ def pack_linear(W: torch.Tensor, transpose: bool, r_pad: int, k_pad: int, scale:
 
 def gemm_nt(segs, N: int, m_tiles: int, device, *, epi: int = EPI_LINEAR, bias=None, relu: bool = False, mask=None,
             inv_scale: float = 1.0, out_f32: Optional[torch.Tensor] = None, n_valid: int = 0, out: Optional[PK] = None,
-            out_off: int = 0, out_scale: float = 1.0, x3: bool = True) -> None:
-    """segs: [(A: PK, a_off, kext, B: PW, b_off, b_row0)], all accumulating into D[rows, N]."""
+            out_off: int = 0, out_scale: float = 1.0, x3: bool = True, colsum: bool = False) -> Optional[torch.Tensor]:
+    """segs: [(A: PK, a_off, kext, B: PW, b_off, b_row0)], all accumulating into D[rows, N].  colsum=True returns the
+    per-tile column sums [m_tiles, N] of the epilogue values (sum over dim 0 = bias gradient)."""
     lib = load()
     g = AonGemm()
     g.mode, g.epi, g.x3, g.nseg, g.N, g.m_tiles = GEMM_NT, epi, int(x3), len(segs), N, m_tiles
@@ -378,8 +379,13 @@ def gemm_nt(segs, N: int, m_tiles: int, device, *, epi: int = EPI_LINEAR, bias=N
         if out.m_tiles != m_tiles or out_off + N > out.feat:
             raise AonError("gemm_nt: packed output out of range")
         g.out_hi, g.out_lo, g.out_feat, g.out_off = out.hi.data_ptr(), _p(out.lo), out.feat, out_off
+    cs = None
+    if colsum:
+        cs = torch.empty(m_tiles, N, dtype=torch.float32, device=device)
+        g.colsum = cs.data_ptr()
     with torch.cuda.device(device):
         _check(lib.aon_gemm_tc(C.byref(g), _stream()), "aon_gemm_tc(NT)")
+    return cs
 
 
 def gemm_tn(A: PK, a_off: int, a_tiles: int, B: PK, b_off: int, N: int, splits: int, x3: bool = True) -> torch.Tensor:

@@ -108,30 +108,27 @@ class _VanillaMLPFn(torch.autograd.Function):
         gB[11] = g_raw[:, :3].sum(0)
         gB[10] = g_raw[:, 3:].sum(0)
 
-        def colsum(G: L.PK, n: int) -> torch.Tensor:
-            return L.colsum_packed(G, 16).sum(0)[:n] / SG
-
         # rgb_layer: the packed gradient has 4 live columns (r, g, b, sigma); W_r^T padded with zero rows ignores sigma
         _wgrad_head(hv, 128, Gr, 3, gW[11], inv_w)
         WrT = L.pack_linear(W[11], True, 128, 16, SW)
         d_hv = L.PK(tiles, 128, dev)
-        L.gemm_nt([(Gr, 0, 16, WrT, 0, 0)], 128, tiles, dev, epi=L.EPI_MASK, mask=(hv, 0), inv_scale=1.0 / SW, out=d_hv)
+        cs = L.gemm_nt([(Gr, 0, 16, WrT, 0, 0)], 128, tiles, dev, epi=L.EPI_MASK, mask=(hv, 0), inv_scale=1.0 / SW, out=d_hv, colsum=True)
         # views_linear.0 : inputs [bottleneck(256), view enc(27)]
         _wgrad(d_hv, 128, bott, 0, 256, 256, gW[8], 0, inv_w)
         _wgrad(d_hv, 128, V, 0, 32, 27, gW[8], 256, inv_w)
-        gB[8] = colsum(d_hv, 128)
+        gB[8] = cs.sum(0) / SG
         WvT = L.pack_linear(W[8], True, 288, 128, SW)
         d_bott = L.PK(tiles, 256, dev)
-        L.gemm_nt([(d_hv, 0, 128, WvT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / SW, out=d_bott)
+        cs = L.gemm_nt([(d_hv, 0, 128, WvT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / SW, out=d_bott, colsum=True)
         # bottleneck_layer and density_layer both read the last trunk activation h[7]
         _wgrad(d_bott, 256, h[7], 0, 256, 256, gW[9], 0, inv_w)
-        gB[9] = colsum(d_bott, 256)
+        gB[9] = cs.sum(0) / SG
         _wgrad_head(h[7], 256, Gs, 1, gW[10], inv_w)
         WbT = L.pack_linear(W[9], True, 256, 256, SW)
         WdT = L.pack_linear(W[10], True, 256, 16, SW)
         d = L.PK(tiles, 256, dev)
-        L.gemm_nt([(d_bott, 0, 256, WbT, 0, 0), (Gs, 0, 16, WdT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[7], 0),
-                  inv_scale=1.0 / SW, out=d)
+        cs = L.gemm_nt([(d_bott, 0, 256, WbT, 0, 0), (Gs, 0, 16, WdT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[7], 0),
+                       inv_scale=1.0 / SW, out=d, colsum=True)
         # trunk, last layer first: pts_linears.i maps x_i -> h[i], x_0 = E, x_i = h[i-1] (+ E for i = 5)
         for i in range(7, -1, -1):
             x = E if i == 0 else h[i - 1]
@@ -139,12 +136,13 @@ class _VanillaMLPFn(torch.autograd.Function):
             _wgrad(d, 256, x, 0, kin, 63 if i == 0 else 256, gW[i], 0, inv_w)
             if i == 5:
                 _wgrad(d, 256, E, 0, 64, 63, gW[5], 256, inv_w)
-            gB[i] = colsum(d, 256)
+            gB[i] = cs.sum(0) / SG                           # column sums of d, produced by the GEMM that wrote d
             if i == 0:
                 break
             WT = L.pack_linear(W[i], True, 320 if i == 5 else 256, 256, SW)
             nd = L.PK(tiles, 256, dev)
-            L.gemm_nt([(d, 0, 256, WT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[i - 1], 0), inv_scale=1.0 / SW, out=nd)
+            cs = L.gemm_nt([(d, 0, 256, WT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[i - 1], 0), inv_scale=1.0 / SW, out=nd,
+                           colsum=True)
             d = nd
         ctx.pk = None
         out = [None, None, None]
@@ -230,15 +228,13 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
         gB = [None] * 20
         g_s, g_c, g_a = torch.zeros_like(s_), torch.zeros_like(c_), torch.zeros_like(a_)
 
-        def colsum(G, n):
-            return L.colsum_packed(G, 16).sum(0)[:n] / SG
-
         def dgrad(segs, n, mask, rows_pad, k_pad):
-            """segs: [(dY, kext, weight index, first row of W^T)] -> PK(tiles, n) masked by `mask`."""
+            """segs: [(dY, kext, weight index, first row of W^T)] -> (PK(tiles, n) masked by `mask`, its column sums / SG)."""
             out = L.PK(tiles, n, dev)
             gs = [(dY, 0, k, L.pack_linear(W[wi], True, rows_pad[j], k_pad[j], SW), 0, r0) for j, (dY, k, wi, r0) in enumerate(segs)]
-            L.gemm_nt(gs, n, tiles, dev, epi=L.EPI_MASK, mask=None if mask is None else (mask, 0), inv_scale=1.0 / SW, out=out)
-            return out
+            cs = L.gemm_nt(gs, n, tiles, dev, epi=L.EPI_MASK, mask=None if mask is None else (mask, 0), inv_scale=1.0 / SW, out=out,
+                           colsum=True)
+            return out, cs.sum(0) / SG
 
         def latent(wi, gb, parts):
             """latent columns of layer wi: dW = gb (x) code, d code = W[:, cols]^T gb."""
@@ -252,27 +248,27 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
         Gs = L.pack_rows(g_raw[:, 3:], M, tiles, 16, SG)
         gB[19], gB[18] = g_raw[:, :3].sum(0), g_raw[:, 3:].sum(0)
         _wgrad_head(hv[3], 128, Gr, 3, gW[19], inv_w)
-        d = dgrad([(Gr, 16, 19, 0)], 128, hv[3], [128], [16])
+        d, cs = dgrad([(Gr, 16, 19, 0)], 128, hv[3], [128], [16])
         for i in (3, 2, 1):
             _wgrad(d, 128, hv[i - 1], 0, 128, 128, gW[13 + i], 0, inv_w)
-            gB[13 + i] = colsum(d, 128)
-            d = dgrad([(d, 128, 13 + i, 0)], 128, hv[i - 1], [128], [128])
+            gB[13 + i] = cs
+            d, cs = dgrad([(d, 128, 13 + i, 0)], 128, hv[i - 1], [128], [128])
         _wgrad(d, 128, bott, 0, 256, 256, gW[13], 0, inv_w)
         _wgrad(d, 128, V, 0, 32, 27, gW[13], 256, inv_w)
-        gB[13] = colsum(d, 128)
+        gB[13] = cs
         latent(13, gB[13], [(283, c_, g_c)])
-        d_bott = dgrad([(d, 128, 13, 0)], 256, None, [416], [128])
+        d_bott, cs = dgrad([(d, 128, 13, 0)], 256, None, [416], [128])
         # ---- trunk ----
         _wgrad(d_bott, 256, h[7], 0, 256, 256, gW[17], 0, inv_w)
-        gB[17] = colsum(d_bott, 256)
+        gB[17] = cs
         _wgrad_head(h[7], 256, Gs, 1, gW[18], inv_w)
-        d = dgrad([(d_bott, 256, 17, 0), (Gs, 16, 18, 0)], 256, h[7], [256, 256], [256, 16])
+        d, cs = dgrad([(d_bott, 256, 17, 0), (Gs, 16, 18, 0)], 256, h[7], [256, 256], [256, 16])
         d5 = None
         for i in range(7, -1, -1):
             wi = 5 + i
             x = E if i == 0 else h[i - 1]
             _wgrad(d, 256, x, 0, 64 if i == 0 else 256, 63 if i == 0 else 256, gW[wi], 0, inv_w)
-            gB[wi] = colsum(d, 256)
+            gB[wi] = cs
             if i == 5:
                 _wgrad(d, 256, E, 0, 64, 63, gW[wi], 256, inv_w)
                 latent(wi, gB[wi], [(319, s_, g_s)])
@@ -280,7 +276,7 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
             if i == 0:
                 latent(wi, gB[wi], [(63, s_, g_s)])
                 break
-            d = dgrad([(d, 256, wi, 0)], 256, h[i - 1], [448 if i == 5 else 256], [256])
+            d, cs = dgrad([(d, 256, wi, 0)], 256, h[i - 1], [448 if i == 5 else 256], [256])
         # ---- encoding -> warped position -> deformation MLP ----
         g_enc = torch.empty(tiles * 128, 63, dtype=torch.float32, device=dev)
         W0T, W5T = L.pack_linear(W[5], True, 192, 256, SW), L.pack_linear(W[10], True, 448, 256, SW)
@@ -290,13 +286,13 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
         Gd = L.pack_rows(g_warped, M, tiles, 16, SG)
         gB[4] = g_warped.sum(0)
         _wgrad_head(hd[3], 128, Gd, 3, gW[4], inv_w)
-        d = dgrad([(Gd, 16, 4, 0)], 128, hd[3], [128], [16])
+        d, cs = dgrad([(Gd, 16, 4, 0)], 128, hd[3], [128], [16])
         for i in (3, 2, 1):
             _wgrad(d, 128, hd[i - 1], 0, 128, 128, gW[i], 0, inv_w)
-            gB[i] = colsum(d, 128)
-            d = dgrad([(d, 128, i, 0)], 128, hd[i - 1], [128], [128])
+            gB[i] = cs
+            d, cs = dgrad([(d, 128, i, 0)], 128, hd[i - 1], [128], [128])
         _wgrad(d, 128, P, 0, 16, 3, gW[0], 0, inv_w)
-        gB[0] = colsum(d, 128)
+        gB[0] = cs
         latent(0, gB[0], [(3, s_, g_s), (131, a_, g_a)])
         ctx.pk = None
         out = [None, None, None, g_s.view(1, -1), g_c.view(1, -1), g_a.view(1, -1)]

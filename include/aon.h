@@ -176,7 +176,8 @@ int aon_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  *               tile to partial[split][a_tiles*128][N]; aon_wgrad_reduce sums the splits in a fixed order.
  * Epilogues (NT): LINEAR  v = acc*inv_scale + bias, optional ReLU;   MASK  v = acc*inv_scale where the hi plane of the
  * forward activation mask_hi = PK(rows, mask_feat) is > 0 else 0 (ReLU adjoint).  v is written as fp32 row-major
- * out_f32[row, 0:n_valid] (row stride ldc) and/or as PK(rows, out_feat) planes at feature offset out_off, times out_scale. */
+ * out_f32[row, 0:n_valid] (row stride ldc) and/or as PK(rows, out_feat) planes at feature offset out_off, times out_scale;
+ * colsum (optional) receives the per-tile column sums of v, summed over tiles by the caller in a fixed order. */
 #define AON_GEMM_MAX_SEG 2
 #define AON_GEMM_NT 0
 #define AON_GEMM_TN 1
@@ -202,6 +203,7 @@ typedef struct AonGemm {
   long ldc;
   void* out_hi;
   void* out_lo;
+  float* colsum;               /* NT, optional: colsum[tile][N] = column sums of v over the tile's 128 rows (bias gradients) */
 } AonGemm;
 int aon_gemm_tc(const AonGemm* gemm, aon_stream_t stream);
 /* fp32 [*, C] rows (row stride ld; packed row m reads source row m / row_div -- per-ray inputs broadcast to their

@@ -73,9 +73,10 @@ def test_gemm_nt_segments_mask_rows(built_lib):
     BT = lib.pack_linear(W, True, 320, 256, 64.0)
     mk = lib.pack_rows(act, M, tiles, 256, 8.0)
     dx = lib.PK(tiles, 256, DEV)
-    lib.gemm_nt([(G, 0, 256, BT, 0, 0)], 256, tiles, DEV, epi=lib.EPI_MASK, mask=(mk, 0), inv_scale=1.0 / 64, out=dx)
+    cs = lib.gemm_nt([(G, 0, 256, BT, 0, 0)], 256, tiles, DEV, epi=lib.EPI_MASK, mask=(mk, 0), inv_scale=1.0 / 64, out=dx, colsum=True)
     want = (dY.double() @ W.double()[:, :256]) * (act > 0)
     assert _rel(dx.to_dense() / 4096.0, want) < 1e-5
+    assert cs.shape == (tiles, 256) and _rel(cs.sum(0) / 4096.0, want.sum(0)) < 1e-5      # fused bias-gradient column sums
     # second row window: the 63 encoding inputs
     dxe = torch.zeros(tiles * 128, 64, device=DEV)
     lib.gemm_nt([(G, 0, 256, BT, 0, 256)], 64, tiles, DEV, epi=lib.EPI_MASK, inv_scale=1.0 / (64 * 4096.0), out_f32=dxe, n_valid=63)
