@@ -367,6 +367,7 @@ def gemm_nt(segs, N: int, m_tiles: int, device, *, epi: int = EPI_LINEAR, bias=N
         g.a_feat[i], g.a_off[i], g.kext[i] = A.feat, a_off, kext
         g.b_feat[i], g.b_off[i], g.b_row0[i] = B.r_pad, b_off, b_row0
     g.relu, g.inv_scale, g.out_scale = int(relu), inv_scale, out_scale
+    g.reserved = int(os.environ.get("AON_GEMM_DEBUG", "0"))
     g.bias = _p(bias)
     if mask is not None:
         mk, moff = mask

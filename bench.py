@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("AON_BENCH_PRECISION", "auto"))
     ap.add_argument("--kind", default="vanilla", choices=["vanilla", "autodecoder"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the extra training-step block")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     return ap.parse_args()
 
@@ -169,6 +170,62 @@ def workload_config(args, precision):
             "weights": "synthetic xavier-like init, density head sharpened (oracle.make_state_dict(sharp=True))",
             "parallelism": "rays sharded contiguously across %d GPU(s); one all-gather of [rays,5] pixels per step" % args.gpus,
             "l2": "256 MiB buffer overwritten between timed iterations (L2 flush)"}
+
+
+def train_block(args, dev, world, rank, rays_o, rays_d):
+    """training_step + backward + gradient all-reduce + optimizer_step of the Lightning-surface module at the reference's
+    per-GPU batch (2048 rays vanilla, model.py:426; 4096 rays sapien_multi, sapien_multi.py:235), randomized sampling,
+    3 warm-up + 10 timed steps, CUDA events, max over ranks.  MLP contractions: tcgen05 GEMMs (train_tc.py)."""
+    import torch
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    from aon_b200 import dist as D
+    from aon_b200 import lib as L
+    from aon_b200 import lit
+    torch.manual_seed(1234 + rank)
+    exp = "vanilla" if args.kind == "vanilla" else "vanilla_autodecoder"
+    Rb = 2048 if args.kind == "vanilla" else 4096
+    s = lit.build_system(SimpleNamespace(exp_type=exp, run_max_steps=100000, white_back=True, N_max_objs=1, N_obj_code_length=128)).to(dev)
+    s.train()
+    s.trainer = SimpleNamespace(global_step=0, is_global_zero=rank == 0)
+    opt = s.configure_optimizers()
+    idx = torch.randperm(rays_o.shape[0], device=dev)[:Rb]
+    batch = {"rays_o": rays_o[idx][None], "rays_d": rays_d[idx][None], "viewdirs": rays_d[idx][None],
+             "target": torch.rand(1, Rb, 3, device=dev)}
+    if args.kind != "vanilla":
+        batch.update(instance_id=torch.tensor([0], device=dev), articulation_id=torch.tensor([3], device=dev))
+
+    def step(i):
+        opt.zero_grad()
+        loss = s.training_step(batch, i)
+        loss.backward()
+        if world > 1:
+            D.allreduce_mean_(opt.flat_grad)
+        s.optimizer_step(0, i, opt, 0, None, False, False, False)
+        s.trainer.global_step += 1
+
+    for i in range(3):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    L.launch_count(reset=True)
+    K = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(3 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / K
+    flop = 3 * Rb * (S0 + S1) * FLOP_PER_SAMPLE[args.kind]
+    return {"value": world * Rb / (ms * 1e-3), "unit": "rays/s (training: forward + backward + all-reduce + Adam)", "ms_per_step": ms,
+            "rays_per_gpu_per_step": Rb, "steps": K, "warmup": 3, "algorithmic_tflops_per_gpu": flop / (ms * 1e-3) / 1e12,
+            "gemm": "tcgen05 kind::f16, fp16 hi+lo operands (3 MMAs per K step), fp32 accumulate" if s.model.train_gemm == "tc" else "library",
+            "aon_launches_per_step": L.launch_count() // K, "grad_allreduce_bytes": opt.flat_grad.numel() * 4 if world > 1 else 0}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -340,6 +397,14 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * R * e2e_steps / dt.item()
 
+    # ---- training step (BASELINE.json configs[3]: ray-sharded training; extra block, not the headline) -------------
+    train = None
+    if not args.no_train:
+        try:
+            train = train_block(args, dev, world, rank, rays_o, rays_d)
+        except Exception as e:       # never lose the headline line to the extra block
+            train = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if rank == 0:
         peaks = {}
         try:
@@ -381,6 +446,8 @@ def main():
         if fast is not None:
             fast["frac"] = fast["achieved_tflops"] / peak
             line["fast_mode"] = fast
+        if train is not None:
+            line["train"] = train
         if not args.no_cpu_baseline and world == 1:
             r = cpu_rays_per_sec(args.kind, args.cpu_seconds)
             line["cpu_baseline"] = {"value": r["value"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}

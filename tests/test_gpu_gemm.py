@@ -109,3 +109,31 @@ def test_gemm_tn_wgrad(built_lib, x3, n_out, n_in, splits):
     # bias gradient
     cs = lib.colsum_packed(G, 4).sum(0) / 4096.0
     assert _rel(cs, dY.double().sum(0)) < (1e-5 if x3 else 3e-3)
+
+
+def test_gemm_nt_persistent_many_tiles(built_lib):
+    """More row tiles than SMs: every persistent CTA walks 2-3 tiles with the ring and the double-buffered TMEM accumulator
+    carried across tiles (forward epilogue, then the dgrad / mask / column-sum epilogue)."""
+    lib = built_lib
+    torch.manual_seed(5)
+    tiles = 333
+    M = tiles * 128 - 50
+    X = torch.randn(M, 256, device=DEV)
+    W = torch.randn(256, 256, device=DEV) / 16
+    b = torch.randn(256, device=DEV)
+    A = lib.pack_rows(X, M, tiles, 256, 8.0)
+    B = lib.pack_linear(W, False, 256, 256, 64.0)
+    out = lib.PK(tiles, 256, DEV)
+    lib.gemm_nt([(A, 0, 256, B, 0, 0)], 256, tiles, DEV, bias=b, relu=True, inv_scale=1.0 / 512, out=out, out_scale=8.0)
+    want = torch.relu(X.double() @ W.double().t() + b.double())
+    got = out.to_dense()[:M] / 8.0
+    assert _rel(got, want) < 1e-5
+    dY = torch.randn(M, 256, device=DEV) * 1e-3
+    G = lib.pack_rows(dY, M, tiles, 256, 1024.0)
+    BT = lib.pack_linear(W, True, 256, 256, 64.0)
+    dx = lib.PK(tiles, 256, DEV)
+    cs = lib.gemm_nt([(G, 0, 256, BT, 0, 0)], 256, tiles, DEV, epi=lib.EPI_MASK, mask=(out, 0), inv_scale=1.0 / 64, out=dx, colsum=True)
+    # the mask is the sign of OUR forward output (a pre-activation within fp32 rounding of zero may round either way)
+    wantd = (dY.double() @ W.double()) * (got > 0)
+    assert _rel(dx.to_dense()[:M] / 1024.0, wantd) < 1e-5
+    assert _rel(cs.sum(0) / 1024.0, wantd.sum(0)) < 1e-5

@@ -31,3 +31,12 @@ flop = 2.0 * M * 256 * 256
 t(lambda: L.gemm_nt([(A, 0, 256, B, 0, 0)], 256, tiles, dev, bias=b, relu=True, inv_scale=1 / 512, out=out, out_scale=8.0), "NT forward 256x256", flop)
 t(lambda: L.gemm_nt([(G, 0, 256, B, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(A, 0), inv_scale=1 / 64, out=out, colsum=True), "NT dgrad+mask+colsum", flop)
 t(lambda: L.gemm_tn(G, 0, 2, A, 0, 256, 148), "TN wgrad 256x256", flop)
+
+# single-plane operands (x3 = False): one MMA per K step, half the operand bytes
+A1 = L.pack_rows(X, M, tiles, 256, 8.0, x3=False); B1 = L.pack_linear(W, False, 256, 256, 64.0, x3=False); out1 = L.PK(tiles, 256, dev, x3=False)
+G1 = L.pack_rows(X * 1e-4, M, tiles, 256, 2048.0, x3=False)
+t(lambda: L.gemm_nt([(A1, 0, 256, B1, 0, 0)], 256, tiles, dev, bias=b, relu=True, inv_scale=1 / 512, out=out1, out_scale=8.0, x3=False), "NT forward f16 (1 plane)", flop)
+t(lambda: L.gemm_tn(G1, 0, 2, A1, 0, 256, 74, x3=False), "TN wgrad f16 (1 plane)", flop)
+t(lambda: L.gemm_tn(G, 0, 2, A, 0, 256, 74), "TN wgrad x3, 74 splits", flop)
+B128 = L.pack_linear(W[:128].contiguous(), False, 128, 256, 64.0); out128 = L.PK(tiles, 128, dev)
+t(lambda: L.gemm_nt([(A, 0, 256, B128, 0, 0)], 128, tiles, dev, inv_scale=1 / 512, out=out128, out_scale=8.0), "NT forward N=128", flop / 2)
