@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
   __shared__ __align__(8) uint64_t s_bar[2 * GT_NS + 1];
   __shared__ uint32_t s_tmem;
   __shared__ float s_colsum[4][256];     // per epilogue warp: column sums of its 32 rows (bias gradients)
+  __shared__ float s_bias[256];
   const AonGemm& g = P.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sm0 = (smem_u32(gt_smem_raw) + 1023u) & ~1023u;
@@ -192,11 +193,38 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
     // ================= epilogue (warps 2..5: TMEM lane quadrant = warp % 4) =================
     const int quad = warp & 3, row = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const long tile = blockIdx.x;
+    // Everything the epilogue needs from global memory is fetched while the main loop runs: the bias vector goes to shared
+    // memory and this thread's row of the ReLU mask is compressed to one bit per feature (8 registers).
+    uint32_t mbits[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    if (g.epi == AON_GEMM_EPI_LINEAR) {
+      for (int c = tid - 64; c < N; c += 128) s_bias[c] = g.bias ? __ldg(g.bias + c) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    } else if (g.epi == AON_GEMM_EPI_MASK && g.mask_hi) {
+      const char* mp = (const char*)g.mask_hi + ((tile * (g.mask_feat / 8) + g.mask_off / 8) * 128 + row) * 16;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        if (cc * 32 < N) {
+          uint32_t bits = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(mp + (long)(cc * 4 + q) * 2048));
+            const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t lo16 = w[j] & 0xffffu, hi16 = w[j] >> 16;       // fp16 > 0: magnitude bits set, sign clear
+              bits |= (uint32_t)((lo16 & 0x7fffu) != 0 && (lo16 & 0x8000u) == 0) << (q * 8 + 2 * j);
+              bits |= (uint32_t)((hi16 & 0x7fffu) != 0 && (hi16 & 0x8000u) == 0) << (q * 8 + 2 * j + 1);
+            }
+          }
+          mbits[cc] = bits;
+        }
+      }
+    }
     if (n_stage_total > 0) {
       gt_wait(accum, 0);
       tc_fence_after();
     }
-    const long tile = blockIdx.x;
     for (int c0 = 0; c0 < N; c0 += 32) {
       uint32_t r[32];
       const int nc = min(32, N - c0);          // 16 or 32
@@ -219,31 +247,18 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
         continue;
       }
       if (g.epi == AON_GEMM_EPI_LINEAR) {
-        if (g.bias) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (i < nc) v[i] += __ldg(g.bias + c0 + i);
-        }
+        for (int i = 0; i < 32; ++i) if (i < nc) v[i] += s_bias[c0 + i];
         if (g.relu) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
       } else {   // AON_GEMM_EPI_MASK: pass where the forward activation (hi plane of PK(rows, mask_feat)) is > 0
-        if (g.mask_hi) {
-          const char* mp = (const char*)g.mask_hi + ((tile * (g.mask_feat / 8) + (g.mask_off + c0) / 8) * 128 + row) * 16;
+        uint32_t bits = 0xffffffffu;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (q * 8 < nc) {
-              const uint4 m = *reinterpret_cast<const uint4*>(mp + (long)q * 2048);
-              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+        for (int cc = 0; cc < 8; ++cc) if (cc == (c0 >> 5)) bits = mbits[cc];      // register select (no local-memory indexing)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t lo16 = w[j] & 0xffffu, hi16 = w[j] >> 16;
-                if (!((lo16 & 0x7fffu) != 0 && (lo16 & 0x8000u) == 0)) v[q * 8 + 2 * j] = 0.f;
-                if (!((hi16 & 0x7fffu) != 0 && (hi16 & 0x8000u) == 0)) v[q * 8 + 2 * j + 1] = 0.f;
-              }
-            }
-          }
-        }
+        for (int i = 0; i < 32; ++i) if (!((bits >> i) & 1u)) v[i] = 0.f;
       }
       if (g.colsum) {
         // 32 columns x 32 lanes -> lane l holds the sum of column c0 + l over this warp's rows: a transpose-reduce butterfly,
