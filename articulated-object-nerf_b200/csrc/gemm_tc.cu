@@ -200,6 +200,10 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
     if (g.epi == AON_GEMM_EPI_LINEAR) {
       for (int c = tid - 64; c < N; c += 128) s_bias[c] = g.bias ? __ldg(g.bias + c) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
+    } else if (g.epi == AON_GEMM_EPI_MASK && g.mask_bits) {
+      const uint32_t* bp = g.mask_bits + (tile * 128 + row) * (long)(N / 32);
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) if (cc * 32 < N) mbits[cc] = __ldg(bp + cc);
     } else if (g.epi == AON_GEMM_EPI_MASK && g.mask_hi) {
       const char* mp = (const char*)g.mask_hi + ((tile * (g.mask_feat / 8) + g.mask_off / 8) * 128 + row) * 16;
 #pragma unroll
@@ -252,6 +256,12 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
         if (g.relu) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          if (g.relu_bits_out) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bits |= (uint32_t)(v[i] > 0.f) << i;
+            g.relu_bits_out[(tile * 128 + row) * (long)(N / 32) + (c0 >> 5)] = bits;
+          }
         }
       } else {   // AON_GEMM_EPI_MASK: pass where the forward activation (hi plane of PK(rows, mask_feat)) is > 0
         uint32_t bits = 0xffffffffu;
@@ -468,6 +478,7 @@ extern "C" int aon_gemm_tc(const AonGemm* gp, aon_stream_t stream) {
   if (g.mode == AON_GEMM_NT) {
     AON_REQUIRE(g.epi == AON_GEMM_EPI_LINEAR || g.epi == AON_GEMM_EPI_MASK, "aon_gemm_tc: NT mode takes a LINEAR or MASK epilogue");
     AON_REQUIRE(g.colsum == nullptr || g.N % 32 == 0, "aon_gemm_tc: colsum needs N to be a multiple of 32");
+    AON_REQUIRE((g.relu_bits_out == nullptr && g.mask_bits == nullptr) || g.N % 32 == 0, "aon_gemm_tc: bit-plane masks need N % 32 == 0");
     grid = dim3((unsigned)g.m_tiles);
   } else {
     AON_REQUIRE(g.epi == AON_GEMM_EPI_PARTIAL && g.partial != nullptr && g.nseg == 1, "aon_gemm_tc: TN mode writes partial tiles");

@@ -58,7 +58,6 @@ __global__ void pos_enc_bwd_kernel(const float* __restrict__ x, const float* __r
 }
 
 // ---- activations + alpha compositing ------------------------------------------------------------------------------------
-// One thread per ray, samples in order: the same fp32 operation sequence as the fused render kernels' epilogue.
 // act_mode 0: rgb = sigmoid(raw), sigma = relu(raw)             (model.py:186-187)
 // act_mode 1: rgb = sigmoid(raw) * 1.002 - 0.001, sigma = softplus(raw - 1)   (model_autodecoder.py:321-323)
 __device__ __forceinline__ float act_rgb(float raw, int mode) {
@@ -69,46 +68,73 @@ __device__ __forceinline__ float act_sigma(float raw, int mode) {
   return mode ? softplusf_ref(__fadd_rn(raw, -1.0f)) : fmaxf(raw, 0.f);
 }
 
-__global__ void composite_fwd_kernel(const float* __restrict__ raw_rgb, const float* __restrict__ raw_sigma,
-                                     const float* __restrict__ t_vals, long t_stride, const float* __restrict__ dirs,
-                                     int R, int S, int white_bkgd, int act_mode, float* __restrict__ comp_rgb,
-                                     float* __restrict__ acc, float* __restrict__ depth, float* __restrict__ weights,
-                                     float* __restrict__ trans_out) {
-  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ray >= R) return;
+// One WARP per ray: lane l handles samples l, l + 32, ...; the exclusive transmittance product (helper.py:171-176) is a
+// multiplicative warp scan per 32-sample chunk with a running carry (the reference's sequential cumprod re-associated: equal
+// to fp32 rounding), the ray sums are warp reductions -- the "warp shuffles in registers" form of the compositing.  All global
+// accesses are coalesced along the sample axis.
+constexpr int COMP_WARPS = 4;
+
+__global__ void __launch_bounds__(COMP_WARPS * 32)
+composite_fwd_kernel(const float* __restrict__ raw_rgb, const float* __restrict__ raw_sigma, const float* __restrict__ t_vals,
+                     long t_stride, const float* __restrict__ dirs, int R, int S, int white_bkgd, int act_mode,
+                     float* __restrict__ comp_rgb, float* __restrict__ acc, float* __restrict__ depth,
+                     float* __restrict__ weights, float* __restrict__ trans_out) {
+  const int lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
+  if (ray >= R) return;                                   // whole warps leave together
   const float dx = dirs[3 * (size_t)ray], dy = dirs[3 * (size_t)ray + 1], dz = dirs[3 * (size_t)ray + 2];
   const float dnorm = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));   // helper.py:168
   const float* tv = t_vals + (size_t)ray * t_stride;
   const float* rr = raw_rgb + (size_t)ray * S * 3;
   const float* rs = raw_sigma + (size_t)ray * S;
-  float trans = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cdepth = 0.f, cacc = 0.f;
-  float t_cur = tv[0];
-#pragma unroll 4
-  for (int s = 0; s < S; ++s) {   // only `trans` is carried from sample to sample: unrolled so the loads and exps overlap
-    const float t_next = (s + 1 < S) ? tv[s + 1] : 0.f;
-    const float r = act_rgb(rr[3 * s + 0], act_mode), g = act_rgb(rr[3 * s + 1], act_mode), b = act_rgb(rr[3 * s + 2], act_mode);
-    const float sigma = act_sigma(rs[s], act_mode);
-    const float delta = (s + 1 < S) ? __fsub_rn(t_next, t_cur) : 1e10f;        // helper.py:160-166
-    const float dist = __fmul_rn(delta, dnorm);
-    const float alpha = __fsub_rn(1.0f, expf(__fmul_rn(-sigma, dist)));          // helper.py:170
-    const float w = __fmul_rn(alpha, trans);                                       // helper.py:176
+  float carry = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cdepth = 0.f, cacc = 0.f;
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    const int s = s0 + lane;
+    const bool valid = s < S;
+    float r = 0.f, g = 0.f, b = 0.f, alpha = 0.f, t_cur = 0.f;
+    if (valid) {
+      t_cur = tv[s];
+      r = act_rgb(rr[3 * s + 0], act_mode); g = act_rgb(rr[3 * s + 1], act_mode); b = act_rgb(rr[3 * s + 2], act_mode);
+      const float sigma = act_sigma(rs[s], act_mode);
+      const float delta = (s + 1 < S) ? __fsub_rn(tv[s + 1], t_cur) : 1e10f;      // helper.py:160-166
+      alpha = __fsub_rn(1.0f, expf(__fmul_rn(-sigma, __fmul_rn(delta, dnorm))));   // helper.py:170
+    }
+    const float f = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;      // helper.py:171-175
+    float p = f;                                            // inclusive product scan over the chunk
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float q = __shfl_up_sync(0xffffffffu, p, o);
+      if (lane >= o) p *= q;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, p, 1);
+    if (lane == 0) excl = 1.0f;
+    const float trans = carry * excl;
+    carry *= __shfl_sync(0xffffffffu, p, 31);
+    const float w = __fmul_rn(alpha, trans);                // helper.py:176
     cr = fmaf(w, r, cr); cg = fmaf(w, g, cg); cb = fmaf(w, b, cb);
     cdepth = fmaf(w, t_cur, cdepth);
     cacc += w;
-    if (weights) weights[(size_t)ray * S + s] = w;
-    if (trans_out) trans_out[(size_t)ray * S + s] = trans;
-    trans = __fmul_rn(trans, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));        // helper.py:171-175
-    t_cur = t_next;
+    if (valid) {
+      if (weights) weights[(size_t)ray * S + s] = w;
+      if (trans_out) trans_out[(size_t)ray * S + s] = trans;
+    }
   }
-  if (isnan(cdepth)) cdepth = INFINITY;                                            // helper.py:179
-  else if (isinf(cdepth)) cdepth = cdepth > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
-  if (white_bkgd) {                                                                // helper.py:185-186
-    const float bg = __fsub_rn(1.0f, cacc);
-    cr += bg; cg += bg; cb += bg;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cr += __shfl_xor_sync(0xffffffffu, cr, o); cg += __shfl_xor_sync(0xffffffffu, cg, o); cb += __shfl_xor_sync(0xffffffffu, cb, o);
+    cdepth += __shfl_xor_sync(0xffffffffu, cdepth, o); cacc += __shfl_xor_sync(0xffffffffu, cacc, o);
   }
-  comp_rgb[3 * (size_t)ray + 0] = cr; comp_rgb[3 * (size_t)ray + 1] = cg; comp_rgb[3 * (size_t)ray + 2] = cb;
-  acc[ray] = cacc;
-  depth[ray] = cdepth;
+  if (lane == 0) {
+    if (isnan(cdepth)) cdepth = INFINITY;                                            // helper.py:179
+    else if (isinf(cdepth)) cdepth = cdepth > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+    if (white_bkgd) {                                                                // helper.py:185-186
+      const float bg = __fsub_rn(1.0f, cacc);
+      cr += bg; cg += bg; cb += bg;
+    }
+    comp_rgb[3 * (size_t)ray + 0] = cr; comp_rgb[3 * (size_t)ray + 1] = cg; comp_rgb[3 * (size_t)ray + 2] = cb;
+    acc[ray] = cacc;
+    depth[ray] = cdepth;
+  }
 }
 
 // Adjoint of composite_fwd_kernel.  With w_s = alpha_s T_s, T_s = prod_{j<s} (1 - alpha_j + 1e-10):
@@ -116,14 +142,16 @@ __global__ void composite_fwd_kernel(const float* __restrict__ raw_rgb, const fl
 //   dL/dc_s     = w_s gC
 //   dL/dalpha_s = dL/dw_s T_s - B_s / (1 - alpha_s + 1e-10),   B_s = sum_{j>s} dL/dw_j w_j
 //   dL/dsigma_s = dL/dalpha_s dist_s exp(-sigma_s dist_s)
-// walked from the last sample to the first with B as a running suffix sum; T_s and w_s come from the forward.
-__global__ void composite_bwd_kernel(const float* __restrict__ raw_rgb, const float* __restrict__ raw_sigma,
-                                     const float* __restrict__ t_vals, long t_stride, const float* __restrict__ dirs,
-                                     const float* __restrict__ weights, const float* __restrict__ trans_in,
-                                     const float* __restrict__ g_rgb, const float* __restrict__ g_acc,
-                                     const float* __restrict__ g_depth, int R, int S, int white_bkgd, int act_mode,
-                                     float* __restrict__ g_raw_rgb, float* __restrict__ g_raw_sigma) {
-  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per ray, chunks of 32 samples from the last to the first; B is an exclusive SUFFIX sum (shuffle-down scan per chunk
+// + carry); T_s and w_s come from the forward.
+__global__ void __launch_bounds__(COMP_WARPS * 32)
+composite_bwd_kernel(const float* __restrict__ raw_rgb, const float* __restrict__ raw_sigma, const float* __restrict__ t_vals,
+                     long t_stride, const float* __restrict__ dirs, const float* __restrict__ weights,
+                     const float* __restrict__ trans_in, const float* __restrict__ g_rgb, const float* __restrict__ g_acc,
+                     const float* __restrict__ g_depth, int R, int S, int white_bkgd, int act_mode,
+                     float* __restrict__ g_raw_rgb, float* __restrict__ g_raw_sigma) {
+  const int lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
   if (ray >= R) return;
   const float dx = dirs[3 * (size_t)ray], dy = dirs[3 * (size_t)ray + 1], dz = dirs[3 * (size_t)ray + 2];
   const float dnorm = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
@@ -136,34 +164,50 @@ __global__ void composite_bwd_kernel(const float* __restrict__ raw_rgb, const fl
               gb = g_rgb ? g_rgb[3 * (size_t)ray + 2] : 0.f;
   const float ga = g_acc ? g_acc[ray] : 0.f, gd = g_depth ? g_depth[ray] : 0.f;
   const float gbg = white_bkgd ? (gr + gg + gb) : 0.f;
-  float B = 0.f;
-#pragma unroll 4
-  for (int s = S - 1; s >= 0; --s) {
-    const float t_cur = tv[s];
-    const float raw_r = rr[3 * s + 0], raw_g = rr[3 * s + 1], raw_b = rr[3 * s + 2], raw_s = rs[s];
-    const float sr = sigmoidf_ref(raw_r), sg = sigmoidf_ref(raw_g), sb = sigmoidf_ref(raw_b);
-    const float k = act_mode ? 1.002f : 1.0f;
-    const float r = act_mode ? __fsub_rn(__fmul_rn(sr, 1.002f), 0.001f) : sr;
-    const float g = act_mode ? __fsub_rn(__fmul_rn(sg, 1.002f), 0.001f) : sg;
-    const float b = act_mode ? __fsub_rn(__fmul_rn(sb, 1.002f), 0.001f) : sb;
-    const float sigma = act_sigma(raw_s, act_mode);
-    const float delta = (s + 1 < S) ? __fsub_rn(tv[s + 1], t_cur) : 1e10f;
-    const float dist = __fmul_rn(delta, dnorm);
-    const float e = expf(__fmul_rn(-sigma, dist));
-    const float alpha = __fsub_rn(1.0f, e);
-    const float w = ww[s], T = tt[s];
-    const float gw = fmaf(gr, r, fmaf(gg, g, fmaf(gb, b, fmaf(gd, t_cur, ga - gbg))));
-    // colour: dL/draw = w gC act'(raw)
-    g_raw_rgb[((size_t)ray * S + s) * 3 + 0] = w * gr * k * sr * (1.0f - sr);
-    g_raw_rgb[((size_t)ray * S + s) * 3 + 1] = w * gg * k * sg * (1.0f - sg);
-    g_raw_rgb[((size_t)ray * S + s) * 3 + 2] = w * gb * k * sb * (1.0f - sb);
-    // density
-    const float galpha = gw * T - B / __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
-    float gsigma = galpha * dist * e;
-    if (e == 0.f) gsigma = 0.f;                                // dist = 1e10 (last sample): 0 * huge stays 0, never nan
-    const float dact = act_mode ? sigmoidf_ref(__fadd_rn(raw_s, -1.0f)) : (raw_s > 0.f ? 1.0f : 0.f);
-    g_raw_sigma[(size_t)ray * S + s] = dact == 0.f ? 0.f : gsigma * dact;
-    B = fmaf(gw, w, B);
+  const float k = act_mode ? 1.002f : 1.0f;
+  float carry = 0.f;                                        // sum of dL/dw_j w_j over the chunks behind this one
+  for (int s0 = ((S - 1) / 32) * 32; s0 >= 0; s0 -= 32) {
+    const int s = s0 + lane;
+    const bool valid = s < S;
+    float x = 0.f, gw = 0.f, w = 0.f, T = 0.f, alpha = 0.f, e = 0.f, dist = 0.f, raw_s = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+    if (valid) {
+      const float t_cur = tv[s];
+      sr = sigmoidf_ref(rr[3 * s + 0]); sg = sigmoidf_ref(rr[3 * s + 1]); sb = sigmoidf_ref(rr[3 * s + 2]);
+      const float r = act_mode ? __fsub_rn(__fmul_rn(sr, 1.002f), 0.001f) : sr;
+      const float g = act_mode ? __fsub_rn(__fmul_rn(sg, 1.002f), 0.001f) : sg;
+      const float b = act_mode ? __fsub_rn(__fmul_rn(sb, 1.002f), 0.001f) : sb;
+      raw_s = rs[s];
+      const float sigma = act_sigma(raw_s, act_mode);
+      const float delta = (s + 1 < S) ? __fsub_rn(tv[s + 1], t_cur) : 1e10f;
+      dist = __fmul_rn(delta, dnorm);
+      e = expf(__fmul_rn(-sigma, dist));
+      alpha = __fsub_rn(1.0f, e);
+      w = ww[s]; T = tt[s];
+      gw = fmaf(gr, r, fmaf(gg, g, fmaf(gb, b, fmaf(gd, t_cur, ga - gbg))));
+      x = gw * w;
+    }
+    float p = x;                                            // inclusive suffix sum over the chunk
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float q = __shfl_down_sync(0xffffffffu, p, o);
+      if (lane + o < 32) p += q;
+    }
+    float B = __shfl_down_sync(0xffffffffu, p, 1);
+    if (lane == 31) B = 0.f;
+    B += carry;
+    carry += __shfl_sync(0xffffffffu, p, 0);
+    if (valid) {
+      // colour: dL/draw = w gC act'(raw)
+      g_raw_rgb[((size_t)ray * S + s) * 3 + 0] = w * gr * k * sr * (1.0f - sr);
+      g_raw_rgb[((size_t)ray * S + s) * 3 + 1] = w * gg * k * sg * (1.0f - sg);
+      g_raw_rgb[((size_t)ray * S + s) * 3 + 2] = w * gb * k * sb * (1.0f - sb);
+      // density
+      const float galpha = gw * T - B / __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+      float gsigma = galpha * dist * e;
+      if (e == 0.f) gsigma = 0.f;                                // dist = 1e10 (last sample): 0 * huge stays 0, never nan
+      const float dact = act_mode ? sigmoidf_ref(__fadd_rn(raw_s, -1.0f)) : (raw_s > 0.f ? 1.0f : 0.f);
+      g_raw_sigma[(size_t)ray * S + s] = dact == 0.f ? 0.f : gsigma * dact;
+    }
   }
 }
 
@@ -217,7 +261,7 @@ extern "C" int aon_composite(const float* raw_rgb, const float* raw_sigma, const
   AON_REQUIRE(t_stride == 0 || t_stride >= S, "aon_composite: bad t_stride %ld", t_stride);
   AON_REQUIRE(act_mode == 0 || act_mode == 1, "aon_composite: bad act_mode %d", act_mode);
   if (R == 0) return AON_OK;
-  composite_fwd_kernel<<<(R + 31) / 32, 32, 0, (cudaStream_t)stream>>>(raw_rgb, raw_sigma, t_vals, t_stride, dirs, R, S, white_bkgd,
+  composite_fwd_kernel<<<(R + COMP_WARPS - 1) / COMP_WARPS, COMP_WARPS * 32, 0, (cudaStream_t)stream>>>(raw_rgb, raw_sigma, t_vals, t_stride, dirs, R, S, white_bkgd,
                                                                        act_mode, comp_rgb, acc, depth, weights, trans);
   AON_LAUNCH_CHECK();
   return AON_OK;
@@ -233,7 +277,7 @@ extern "C" int aon_composite_backward(const float* raw_rgb, const float* raw_sig
   AON_REQUIRE(t_stride == 0 || t_stride >= S, "aon_composite_backward: bad t_stride %ld", t_stride);
   AON_REQUIRE(act_mode == 0 || act_mode == 1, "aon_composite_backward: bad act_mode %d", act_mode);
   if (R == 0) return AON_OK;
-  composite_bwd_kernel<<<(R + 31) / 32, 32, 0, (cudaStream_t)stream>>>(raw_rgb, raw_sigma, t_vals, t_stride, dirs, weights, trans,
+  composite_bwd_kernel<<<(R + COMP_WARPS - 1) / COMP_WARPS, COMP_WARPS * 32, 0, (cudaStream_t)stream>>>(raw_rgb, raw_sigma, t_vals, t_stride, dirs, weights, trans,
                                                                        g_comp_rgb, g_acc, g_depth, R, S, white_bkgd, act_mode,
                                                                        g_raw_rgb, g_raw_sigma);
   AON_LAUNCH_CHECK();

@@ -297,17 +297,19 @@ class AonGemm(C.Structure):
                 ("a_tiles", _i), ("splits", _i), ("tiles_per_split", _i), ("relu", _i),
                 ("partial", _vp), ("inv_scale", _f), ("out_scale", _f),
                 ("n_valid", _i), ("mask_feat", _i), ("mask_off", _i), ("out_feat", _i), ("out_off", _i), ("reserved", _i),
-                ("bias", _vp), ("mask_hi", _vp), ("out_f32", _vp), ("ldc", _l), ("out_hi", _vp), ("out_lo", _vp), ("colsum", _vp)]
+                ("bias", _vp), ("mask_hi", _vp), ("out_f32", _vp), ("ldc", _l), ("out_hi", _vp), ("out_lo", _vp), ("colsum", _vp),
+                ("relu_bits_out", _vp), ("mask_bits", _vp)]
 
 
 class PK:
     """Activation / gradient matrix [m_tiles*128, feat] as 16-bit hi (+ lo) planes in the k-group packed layout
     [rows/128][feat/8][128][8] (see csrc/gemm_tc.cu)."""
-    __slots__ = ("hi", "lo", "m_tiles", "feat")
+    __slots__ = ("hi", "lo", "m_tiles", "feat", "bits")
 
     def __init__(self, m_tiles: int, feat: int, device, x3: bool = True):
         assert feat % 8 == 0
         self.m_tiles, self.feat = m_tiles, feat
+        self.bits = None       # [rows, feat/32] int32 ReLU mask bit plane, written by the forward GEMM that produced this tensor
         self.hi = torch.empty(m_tiles * feat * 128, dtype=torch.float16, device=device)
         self.lo = torch.empty_like(self.hi) if x3 else None
 
@@ -371,7 +373,10 @@ def gemm_nt(segs, N: int, m_tiles: int, device, *, epi: int = EPI_LINEAR, bias=N
     g.bias = _p(bias)
     if mask is not None:
         mk, moff = mask
-        g.mask_hi, g.mask_feat, g.mask_off = mk.hi.data_ptr(), mk.feat, moff
+        if mk.bits is not None and moff == 0 and mk.feat == N:
+            g.mask_bits = mk.bits.data_ptr()          # 32 B per row instead of a 512 B activation row
+        else:
+            g.mask_hi, g.mask_feat, g.mask_off = mk.hi.data_ptr(), mk.feat, moff
     if out_f32 is not None:
         if out_f32.shape[0] < m_tiles * 128 or out_f32.stride(1) != 1:
             raise AonError("gemm_nt: out_f32 must hold m_tiles*128 rows")
@@ -380,6 +385,9 @@ def gemm_nt(segs, N: int, m_tiles: int, device, *, epi: int = EPI_LINEAR, bias=N
         if out.m_tiles != m_tiles or out_off + N > out.feat:
             raise AonError("gemm_nt: packed output out of range")
         g.out_hi, g.out_lo, g.out_feat, g.out_off = out.hi.data_ptr(), _p(out.lo), out.feat, out_off
+        if relu and epi == EPI_LINEAR and out_off == 0 and out.feat == N and N % 32 == 0:
+            out.bits = torch.empty(m_tiles * 128, N // 32, dtype=torch.int32, device=device)
+            g.relu_bits_out = out.bits.data_ptr()
     cs = None
     if colsum:
         cs = torch.empty(m_tiles, N, dtype=torch.float32, device=device)

@@ -177,7 +177,9 @@ int aon_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * Epilogues (NT): LINEAR  v = acc*inv_scale + bias, optional ReLU;   MASK  v = acc*inv_scale where the hi plane of the
  * forward activation mask_hi = PK(rows, mask_feat) is > 0 else 0 (ReLU adjoint).  v is written as fp32 row-major
  * out_f32[row, 0:n_valid] (row stride ldc) and/or as PK(rows, out_feat) planes at feature offset out_off, times out_scale;
- * colsum (optional) receives the per-tile column sums of v, summed over tiles by the caller in a fixed order. */
+ * colsum (optional) receives the per-tile column sums of v, summed over tiles by the caller in a fixed order.  A forward
+ * GEMM can also emit the ReLU mask as a bit plane (relu_bits_out, 32 B per row for N = 256) that the dgrad GEMM reads
+ * through mask_bits instead of re-reading a whole activation plane. */
 #define AON_GEMM_MAX_SEG 2
 #define AON_GEMM_NT 0
 #define AON_GEMM_TN 1
@@ -204,6 +206,8 @@ typedef struct AonGemm {
   void* out_hi;
   void* out_lo;
   float* colsum;               /* NT, optional: colsum[tile][N] = column sums of v over the tile's 128 rows (bias gradients) */
+  uint32_t* relu_bits_out;     /* LINEAR + relu, optional (N % 32 == 0): bit c%32 of word [row][c/32] = (v[row][c] > 0) */
+  const uint32_t* mask_bits;   /* MASK, optional alternative to mask_hi: the [rows][N/32] bit plane a forward GEMM wrote */
 } AonGemm;
 int aon_gemm_tc(const AonGemm* gemm, aon_stream_t stream);
 /* fp32 [*, C] rows (row stride ld; packed row m reads source row m / row_div -- per-ray inputs broadcast to their

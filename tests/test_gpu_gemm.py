@@ -132,6 +132,9 @@ def test_gemm_nt_persistent_many_tiles(built_lib):
     G = lib.pack_rows(dY, M, tiles, 256, 1024.0)
     BT = lib.pack_linear(W, True, 256, 256, 64.0)
     dx = lib.PK(tiles, 256, DEV)
+    assert out.bits is not None and out.bits.shape == (tiles * 128, 8)           # ReLU mask bit plane from the forward epilogue
+    bits = ((out.bits[:M, :, None] >> torch.arange(32, device=DEV)) & 1).reshape(M, 256).bool()
+    assert torch.equal(bits, got > 0)
     cs = lib.gemm_nt([(G, 0, 256, BT, 0, 0)], 256, tiles, DEV, epi=lib.EPI_MASK, mask=(out, 0), inv_scale=1.0 / 64, out=dx, colsum=True)
     # the mask is the sign of OUR forward output (a pre-activation within fp32 rounding of zero may round either way)
     wantd = (dY.double() @ W.double()) * (got > 0)
