@@ -453,6 +453,8 @@ __global__ void __launch_bounds__(128) colsum_packed_kernel(const uint4* __restr
 
 using namespace aon;
 
+extern "C" size_t aon_gemm_struct_size(void) { return sizeof(AonGemm); }
+
 extern "C" int aon_gemm_tc(const AonGemm* gp, aon_stream_t stream) {
   AON_REQUIRE(gp != nullptr, "aon_gemm_tc: null descriptor");
   const AonGemm& g = *gp;

@@ -42,6 +42,7 @@ SYMBOLS = {
     "aon_composite_backward": (_i, [_fp, _fp, _fp, _l, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),
     "aon_adam_step": (_i, [_fp, _fp, _fp, _fp, _l, _d, _d, _d, _d, _l, _d, _vp]),
     "aon_gemm_tc": (_i, [_vp, _vp]),
+    "aon_gemm_struct_size": (_sz, []),
     "aon_pack_rows": (_i, [_fp, _l, _i, _l, _i, _i, _i, _f, _vp, _vp, _vp]),
     "aon_pack_linear": (_i, [_fp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "aon_wgrad_reduce": (_i, [_fp, _i, _i, _i, _f, _fp, _l, _i, _i, _i, _i, _vp]),

@@ -210,6 +210,8 @@ typedef struct AonGemm {
   const uint32_t* mask_bits;   /* MASK, optional alternative to mask_hi: the [rows][N/32] bit plane a forward GEMM wrote */
 } AonGemm;
 int aon_gemm_tc(const AonGemm* gemm, aon_stream_t stream);
+/* sizeof(AonGemm) as this library was compiled: bindings in other languages check their mirror of the struct against it. */
+size_t aon_gemm_struct_size(void);
 /* fp32 [*, C] rows (row stride ld; packed row m reads source row m / row_div -- per-ray inputs broadcast to their
  * samples) -> PK(m_tiles*128, c_pad) hi (+ lo if non-NULL) times scale; rows >= M and columns >= C are zero. */
 int aon_pack_rows(const float* src, long ld, int C, long M, int row_div, int m_tiles, int c_pad, float scale,

@@ -59,3 +59,18 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_gemm_descriptor_mirror_and_training_argument_errors(built_lib):
+    """The ctypes mirror of `struct AonGemm` has the C struct's size, and the training entry points reject bad arguments
+    before touching CUDA."""
+    lib = built_lib.load()
+    assert ctypes.sizeof(built_lib.AonGemm) == lib.aon_gemm_struct_size()
+    assert lib.aon_gemm_tc(None, None) == -1 and b"null" in lib.aon_last_error()
+    g = built_lib.AonGemm()
+    g.mode, g.N, g.nseg = 0, 24, 1                     # N must be a multiple of 16
+    assert lib.aon_gemm_tc(ctypes.byref(g), None) == -1 and b"multiple of 16" in lib.aon_last_error()
+    assert lib.aon_composite(None, None, None, 0, None, 1, 65, 1, 0, None, None, None, None, None, None) == -1
+    assert lib.aon_pos_enc(None, 1, 10, None, None) == -1
+    assert lib.aon_adam_step(None, None, None, None, 1, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
+    assert lib.aon_pack_rows(None, 1, 1, 1, 1, 1, 8, ctypes.c_float(1.0), None, None, None) == -1
