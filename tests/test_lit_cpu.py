@@ -39,3 +39,24 @@ def test_unknown_exp_type_rejected(built_lib):
     from aon_b200 import lit
     with pytest.raises(ValueError):
         lit.build_system(_hp(exp_type="vanilla_ae_art"))
+
+
+def test_latent_fold_equals_concat_formulation(built_lib):
+    """train_tc._fold: bias + W[:, cols] @ code equals the reference's broadcast-and-concatenate formulation
+    (model_autodecoder.py:186-198): W @ [x, shape, art] + b with x = 0."""
+    from aon_b200 import train_tc
+    torch.manual_seed(0)
+    W, b = torch.randn(128, 163), torch.randn(128)
+    shape, art = torch.randn(1, 128), torch.randn(1, 32)
+    got = train_tc._fold(b, W, [(3, shape.reshape(-1)), (131, art.reshape(-1))])
+    want = torch.nn.functional.linear(torch.cat([torch.zeros(1, 3), shape, art], -1), W, b)[0]
+    assert torch.allclose(got, want, atol=1e-5)
+    assert train_tc._pad(63, 16) == 64 and train_tc._pad(319, 16) == 320 and train_tc._pad(256, 16) == 256
+
+
+def test_flat_adam_refuses_cpu_parameters(built_lib):
+    """No CPU fallback on the training path either: the optimizer fails loudly on CPU parameters."""
+    from aon_b200 import lib, lit
+    s = lit.LitNeRF(_hp())
+    with pytest.raises(lib.AonError):
+        s.configure_optimizers()
