@@ -332,6 +332,247 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
+// ---- persistent NT kernel (the large forward / dgrad GEMMs: N = 128 or 256, at least one row tile per SM) -------------------
+// One CTA per SM walks row tiles blockIdx.x, + gridDim.x, ...; the 4-stage ring runs continuously across tiles and the
+// accumulator is double buffered in TMEM (2 x N columns), so the epilogue of tile i overlaps the loads and MMAs of tile i + 1.
+// EIGHT epilogue warps (two per TMEM lane quadrant, even / odd 32-column chunks) keep the epilogue shorter than the main loop --
+// with four (and global-memory reads on its critical path) the first persistent version was epilogue-bound and slower than the
+// two-CTAs-per-SM kernel above (tools/experiments/README.md).
+constexpr int GP_NS = 4;
+constexpr int GP_EPI_WARPS = 8;
+constexpr int GP_THREADS = 64 + 32 * GP_EPI_WARPS;                 // 320
+constexpr int GP_EPI_THREADS = 32 * GP_EPI_WARPS;                  // 256
+constexpr uint32_t GP_SMEM = GP_NS * GT_STAGE + 1024;
+
+__global__ void __launch_bounds__(GP_THREADS, 1) gemm_tc_nt_persistent_kernel(const GtParams P) {
+  extern __shared__ unsigned char gt_smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar[2 * GP_NS + 4];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_colsum[2][4][256];  // [tile parity][lane quadrant]: column sums of the quadrant's 32 rows (bias gradients)
+  __shared__ float s_bias[256];
+  const AonGemm& g = P.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sm0 = (smem_u32(gt_smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (GP_NS + s); };
+  auto acc_full = [&](int b) { return bar0 + 8u * (2 * GP_NS + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (2 * GP_NS + 2 + b); };
+  const int N = g.N;                                   // 128 or 256
+  const uint32_t buf_cols = (uint32_t)N, tmem_cols = 2u * buf_cols;
+  const bool x3 = g.x3 != 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < GP_NS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), GP_EPI_THREADS); }
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(smem_u32(&s_tmem), tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  const long tile0 = blockIdx.x, tile_step = gridDim.x, tile_end = g.m_tiles;
+
+  if (warp == 0) {
+    // ================= producer =================
+    long it = 0;
+    const int planes = x3 ? 2 : 1;
+    for (long tile = tile0; tile < tile_end; tile += tile_step) {
+      for (int sgi = 0; sgi < g.nseg; ++sgi) {
+        const char* a_pl[2] = {(const char*)g.a_hi[sgi], (const char*)g.a_lo[sgi]};
+        const char* b_pl[2] = {(const char*)g.b_hi[sgi], (const char*)g.b_lo[sgi]};
+        const long a_tile = tile * (long)(g.a_feat[sgi] / 8) * 2048;
+        for (int k0 = 0; k0 < g.kext[sgi]; k0 += GT_KC, ++it) {
+          const int s = (int)(it % GP_NS);
+          const int kc = min(GT_KC, g.kext[sgi] - k0), nkg = kc / 8;
+          gt_wait(empty(s), (uint32_t)(((it / GP_NS) & 1) ^ 1));
+          const uint32_t a_bytes = (uint32_t)nkg * 2048u, b_piece = (uint32_t)N * 16u;
+          if (lane == 0) mbar_arrive_expect_tx(full(s), (uint32_t)planes * (a_bytes + (uint32_t)nkg * b_piece));
+          __syncwarp();
+          const uint32_t st = sm0 + (uint32_t)s * GT_STAGE;
+          const int per_plane = 1 + nkg;
+          for (int p = lane; p < planes * per_plane; p += 32) {
+            const int pl = p / per_plane, q = p % per_plane;
+            if (q == 0) {
+              bulk_g2s(st + (uint32_t)pl * GT_A_PLANE, a_pl[pl] + a_tile + (long)((g.a_off[sgi] + k0) / 8) * 2048, a_bytes, full(s));
+            } else {
+              const int kg = q - 1;
+              bulk_g2s(st + 2 * GT_A_PLANE + (uint32_t)pl * GT_B_PLANE + (uint32_t)kg * b_piece,
+                       b_pl[pl] + ((long)((g.b_off[sgi] + k0) / 8 + kg) * g.b_feat[sgi] + g.b_row0[sgi]) * 16, b_piece, full(s));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_f16(128, N, 0);
+      long it = 0, lt = 0;
+      for (long tile = tile0; tile < tile_end; tile += tile_step, ++lt) {
+        const int b = (int)(lt & 1);
+        gt_wait(acc_empty(b), (uint32_t)(((lt >> 1) & 1) ^ 1));     // the epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)b * buf_cols;
+        uint32_t accumulate = 0;
+        for (int sgi = 0; sgi < g.nseg; ++sgi)
+          for (int k0 = 0; k0 < g.kext[sgi]; k0 += GT_KC, ++it) {
+            const int s = (int)(it % GP_NS);
+            gt_wait(full(s), (uint32_t)((it / GP_NS) & 1));
+            tc_fence_after();
+            const uint32_t st = sm0 + (uint32_t)s * GT_STAGE;
+            const uint32_t a_hi = st, a_lo = st + GT_A_PLANE, b_hi = st + 2 * GT_A_PLANE, b_lo = b_hi + GT_B_PLANE;
+            const int kc = min(GT_KC, g.kext[sgi] - k0);
+            for (int kk = 0; kk < kc / 16; ++kk) {
+              const uint32_t a_off = (uint32_t)kk * 4096u, b_off = (uint32_t)kk * 2u * (uint32_t)N * 16u, b_lbo = (uint32_t)N * 16u;
+              mma_f16_ss(d_tmem, smem_desc(a_hi + a_off, 2048u, 128u), smem_desc(b_hi + b_off, b_lbo, 128u), idesc, accumulate);
+              accumulate = 1;
+              if (x3) {
+                mma_f16_ss(d_tmem, smem_desc(a_lo + a_off, 2048u, 128u), smem_desc(b_hi + b_off, b_lbo, 128u), idesc, 1);
+                mma_f16_ss(d_tmem, smem_desc(a_hi + a_off, 2048u, 128u), smem_desc(b_lo + b_off, b_lbo, 128u), idesc, 1);
+              }
+            }
+            mma_commit(empty(s));
+          }
+        mma_commit(acc_full(b));
+      }
+    }
+  } else {
+    // ================= epilogue: warps 2..9, TMEM lane quadrant = warp % 4, chunk parity = (warp - 2) / 4 =================
+    const int quad = warp & 3, half = (warp - 2) >> 2, row = quad * 32 + lane, e = tid - 64;
+    if (g.epi == AON_GEMM_EPI_LINEAR) {
+      for (int c = e; c < N; c += GP_EPI_THREADS) s_bias[c] = g.bias ? __ldg(g.bias + c) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    const int n_chunks = N / 32;
+    long lt = 0;
+    for (long tile = tile0; tile < tile_end; tile += tile_step, ++lt) {
+      const int ab = (int)(lt & 1);
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)ab * buf_cols;
+      // the ReLU mask of this tile's row, one bit per feature, fetched before the accumulator is ready
+      uint32_t mbits[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (g.epi == AON_GEMM_EPI_MASK && g.mask_bits) {
+        const uint32_t* bp = g.mask_bits + (tile * 128 + row) * (long)(N / 32);
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) if (cc < n_chunks) mbits[cc] = __ldg(bp + cc);
+      } else if (g.epi == AON_GEMM_EPI_MASK && g.mask_hi) {
+        const char* mp = (const char*)g.mask_hi + ((tile * (g.mask_feat / 8) + g.mask_off / 8) * 128 + row) * 16;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          if (cc < n_chunks && (cc & 1) == half) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 m = __ldg(reinterpret_cast<const uint4*>(mp + (long)(cc * 4 + q) * 2048));
+              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t lo16 = w[j] & 0xffffu, hi16 = w[j] >> 16;
+                bits |= (uint32_t)((lo16 & 0x7fffu) != 0 && (lo16 & 0x8000u) == 0) << (q * 8 + 2 * j);
+                bits |= (uint32_t)((hi16 & 0x7fffu) != 0 && (hi16 & 0x8000u) == 0) << (q * 8 + 2 * j + 1);
+              }
+            }
+            mbits[cc] = bits;
+          }
+        }
+      }
+      gt_wait(acc_full(ab), (uint32_t)((lt >> 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int cj = 0; cj < 4; ++cj) {
+        const int ci = 2 * cj + half;
+        if (ci < n_chunks) {
+          const int c0 = ci * 32;
+          uint32_t r[32];
+          tmem_ld32(lane_base + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (ci + 2 >= n_chunks) {                  // this warp's last read of the buffer: hand it back to the MMA issuer
+            tc_fence_before();
+            mbar_arrive(acc_empty(ab));
+          }
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * g.inv_scale;
+          if (g.epi == AON_GEMM_EPI_LINEAR) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += s_bias[c0 + i];
+            if (g.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+              if (g.relu_bits_out) {
+                uint32_t bits = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) bits |= (uint32_t)(v[i] > 0.f) << i;
+                g.relu_bits_out[(tile * 128 + row) * (long)(N / 32) + ci] = bits;
+              }
+            }
+          } else {
+            const uint32_t bits = half ? mbits[2 * cj + 1] : mbits[2 * cj];      // cj is unrolled: a register select
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (!((bits >> i) & 1u)) v[i] = 0.f;
+          }
+          if (g.colsum) {
+            float t[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = v[i];
+#pragma unroll
+            for (int k = 16; k >= 1; k >>= 1) {
+              const bool up = (lane & k) != 0;
+#pragma unroll
+              for (int i = 0; i < k; ++i) {
+                const float send = up ? t[i] : t[i + k];
+                const float keep = up ? t[i + k] : t[i];
+                t[i] = keep + __shfl_xor_sync(0xffffffffu, send, k);
+              }
+            }
+            s_colsum[ab][quad][c0 + lane] = t[0];
+          }
+          if (g.out_f32) {
+            float* dst = g.out_f32 + (tile * 128 + row) * g.ldc;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (c0 + i < g.n_valid) dst[c0 + i] = v[i];
+          }
+          if (g.out_hi) {
+            const long base = ((tile * (g.out_feat / 8) + (g.out_off + c0) / 8) * 128 + row) * 16;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float s[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) s[j] = v[q * 8 + j] * g.out_scale;
+              uint4 h;
+              h.x = pack_h2(s[0], s[1]); h.y = pack_h2(s[2], s[3]); h.z = pack_h2(s[4], s[5]); h.w = pack_h2(s[6], s[7]);
+              *reinterpret_cast<uint4*>((char*)g.out_hi + base + (long)q * 2048) = h;
+              if (g.out_lo) {
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+                float l[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  l[2 * j] = s[2 * j] - __half2float(__ushort_as_half((unsigned short)(hw[j] & 0xffffu)));
+                  l[2 * j + 1] = s[2 * j + 1] - __half2float(__ushort_as_half((unsigned short)(hw[j] >> 16)));
+                }
+                uint4 lo;
+                lo.x = pack_h2(l[0], l[1]); lo.y = pack_h2(l[2], l[3]); lo.z = pack_h2(l[4], l[5]); lo.w = pack_h2(l[6], l[7]);
+                *reinterpret_cast<uint4*>((char*)g.out_lo + base + (long)q * 2048) = lo;
+              }
+            }
+          }
+        }
+      }
+      if (g.colsum) {
+        // the eight epilogue warps meet once per tile; s_colsum is double buffered by tile parity, so a warp that runs ahead
+        // into the next tile writes the other half
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = e; c < N; c += GP_EPI_THREADS)
+          g.colsum[tile * N + c] = (s_colsum[ab][0][c] + s_colsum[ab][1][c]) + (s_colsum[ab][2][c] + s_colsum[ab][3][c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
 // ---- packing ------------------------------------------------------------------------------------------------------------
 // fp32 [rows_in, C] (row stride ld; source row of packed row m is m / row_div) -> PK(m_tiles*128, c_pad) hi (+ lo) * scale;
 // rows >= M and columns >= C are zero.
@@ -488,9 +729,18 @@ extern "C" int aon_gemm_tc(const AonGemm* gp, aon_stream_t stream) {
                 "aon_gemm_tc: bad TN decomposition");
     grid = dim3((unsigned)g.a_tiles, (unsigned)g.splits);
   }
-  AON_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
   GtParams P;
   P.g = g;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (g.mode == AON_GEMM_NT && (g.N == 128 || g.N == 256) && g.m_tiles >= 2 * sms && !(g.reserved & 16)) {
+    // the large forward / dgrad GEMMs: persistent kernel, one CTA per SM
+    AON_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_nt_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM));
+    gemm_tc_nt_persistent_kernel<<<sms, GP_THREADS, GP_SMEM, (cudaStream_t)stream>>>(P);
+    AON_LAUNCH_CHECK();
+    return AON_OK;
+  }
+  AON_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
   gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM, (cudaStream_t)stream>>>(P);
   AON_LAUNCH_CHECK();
   return AON_OK;

@@ -140,3 +140,15 @@ def test_gemm_nt_persistent_many_tiles(built_lib):
     wantd = (dY.double() @ W.double()) * (got > 0)
     assert _rel(dx.to_dense()[:M] / 1024.0, wantd) < 1e-5
     assert _rel(cs.sum(0) / 1024.0, wantd.sum(0)) < 1e-5
+    # the same through a mask given as an activation plane (no bit plane) and two segments (skip concat shape)
+    act = torch.relu(torch.randn(M, 256, device=DEV))
+    mk = lib.pack_rows(act, M, tiles, 256, 8.0)
+    E = torch.randn(M, 63, device=DEV)
+    Ae = lib.pack_rows(E, M, tiles, 64, 8.0)
+    W2 = torch.randn(256, 319, device=DEV) / 18
+    B2 = lib.pack_linear(W2, False, 256, 320, 64.0)
+    o2 = lib.PK(tiles, 256, DEV)
+    lib.gemm_nt([(A, 0, 256, B2, 0, 0), (Ae, 0, 64, B2, 256, 0)], 256, tiles, DEV, epi=lib.EPI_MASK, mask=(mk, 0), inv_scale=1.0 / 512,
+                out=o2, out_scale=8.0)
+    want2 = (torch.cat([X, E], 1).double() @ W2.double().t()) * (act > 0)
+    assert _rel(o2.to_dense()[:M] / 8.0, want2) < 1e-5

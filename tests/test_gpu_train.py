@@ -197,13 +197,15 @@ def test_flat_adam_training_updates_packed_weights(built_lib):
     assert (after - before).abs().max() > 1e-4
 
 
-def test_vanilla_mlp_tc_matches_autograd(built_lib):
+@pytest.mark.parametrize("R", [37, 600])
+def test_vanilla_mlp_tc_matches_autograd(built_lib, R):
     """train_tc.vanilla_mlp (tcgen05 forward / dgrad / wgrad GEMMs, hi+lo fp16 operands) against fp64 torch autograd of
-    NeRFMLP.forward (model.py:95-120) on the same inputs: outputs and every parameter gradient to fp32 grade."""
+    NeRFMLP.forward (model.py:95-120) on the same inputs: outputs and every parameter gradient to fp32 grade.
+    R = 37: 19 row tiles, ragged (one tile per CTA); R = 600: 305 row tiles -> the persistent kernel, 2-3 tiles per CTA."""
     from aon_b200 import nerf, train_tc
     torch.manual_seed(0)
     dev = torch.device(DEV)
-    R, S = 37, 65                                             # M = 2405: ragged last row tile
+    S = 65
     mlp = nerf.NeRFMLP(0, 10, 4).to(dev)
     with torch.no_grad():
         for p in mlp.parameters():
@@ -220,8 +222,19 @@ def test_vanilla_mlp_tc_matches_autograd(built_lib):
     rr, rs = ref(enc.double().cpu(), view.double().cpu())
     ((rr * g[..., :3].double().cpu()).sum() + (rs * g[..., 3:].double().cpu()).sum()).backward()
     assert _rel(raw_rgb, rr) < 1e-5 and _rel(raw_sigma, rs) < 1e-5
+    # Yardstick for the gradients: the same module through torch fp32 library GEMMs.  A pre-activation within fp32 rounding
+    # of zero takes either side of the ReLU; one such sample changes a weight-gradient entry (a sum of ~sqrt(M) magnitude)
+    # by ~1 / sqrt(M) of itself, so with M = 39 000 samples ANY fp32 evaluation differs from fp64 by ~1e-3 in a few entries.
+    for p in mlp.parameters():
+        p.grad = None
+    r32, s32 = mlp(enc, view)
+    ((r32 * g[..., :3]).sum() + (s32 * g[..., 3:]).sum()).backward()
+    g32 = {n: p.grad for n, p in mlp.named_parameters()}
+    floor = max(_rel(g32[n], p.grad, floor=1e-12) for n, p in ref.named_parameters())
+    tol = max(2e-5, 8 * floor)
+    print("vanilla MLP R=%d: fp32 torch vs fp64 floor %.2e -> bar %.2e" % (R, floor, tol))
     for n, p in ref.named_parameters():
-        assert _rel(got[n], p.grad, floor=1e-12) < 2e-5, n
+        assert _rel(got[n], p.grad, floor=1e-12) < tol, (n, _rel(got[n], p.grad, floor=1e-12), tol)
 
 
 def test_autodecoder_mlp_tc_matches_autograd(built_lib):
