@@ -160,7 +160,7 @@ def run_reference(args):
             "cpu_baseline": {"value": r["value"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, precision):
@@ -231,8 +231,30 @@ def train_block(args, dev, world, rank, rays_o, rays_d):
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
+_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle to the real stdout and point fd 1 at stderr, so anything a
+    library writes to stdout (NCCL prints its version banner there at NCCL_DEBUG >= VERSION, torchrun helpers, ...) cannot
+    get in front of it."""
+    global _OUT
+    if _OUT is None:
+        sys.stdout.flush()
+        _OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _OUT
+
+
+def emit(line: dict) -> None:
+    out = claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -250,8 +272,6 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"     # NCCL prints its version banner on stdout; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     lib = L.load()
@@ -451,7 +471,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             r = cpu_rays_per_sec(args.kind, args.cpu_seconds)
             line["cpu_baseline"] = {"value": r["value"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
