@@ -52,6 +52,18 @@ def test_sass_is_sm100a(built_lib):
     assert "sm_100a" in out, out
 
 
+def test_sass_has_the_blackwell_instructions(built_lib):
+    """The tensor-core paths really are tcgen05 / TMA code: UTCHMMA (tcgen05.mma kind::f16, incl. the 2-CTA form of the fused
+    render kernel), LDTM (tcgen05.ld), UBLKCP (cp.async.bulk) in the SASS of the shipped library."""
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP"):
+        assert sass.count(mnemonic) > 0, mnemonic
+    assert "UTCHMMA.2CTA" in sass
+    for fn in ("render_tc_kernel", "gemm_tc_kernel", "gemm_tc_nt_persistent_kernel"):
+        assert fn in sass, fn
+
+
 def test_product_package_does_not_import_oracle():
     pkg = os.path.join(ROOT, "articulated-object-nerf_b200")
     for dirpath, _, files in os.walk(pkg):
