@@ -338,6 +338,10 @@ class Trainer:
     def fit(self, system: _LitCommon, batches) -> _LitCommon:
         system.trainer = self
         opt = getattr(system, "_optimizer", None) or system.configure_optimizers()
+        if getattr(system, "_optimizer", None) is None and D.world()[1] > 1:
+            torch.distributed.broadcast(opt.flat, src=0)     # DDP start state: every rank trains rank 0's initial weights
+            for p in opt.param_groups[0]["params"]:
+                torch.autograd.graph.increment_version(p)    # the packed-weight cache keys on parameter versions
         system._optimizer = opt                          # Adam moments survive repeated fit() calls
         system.train()
         for batch_idx, batch in enumerate(batches):

@@ -182,13 +182,14 @@ def train_block(args, dev, world, rank, rays_o, rays_d):
     from aon_b200 import dist as D
     from aon_b200 import lib as L
     from aon_b200 import lit
-    torch.manual_seed(1234 + rank)
+    torch.manual_seed(1234)                       # identical initial weights on every rank (DDP semantics) ...
     exp = "vanilla" if args.kind == "vanilla" else "vanilla_autodecoder"
     Rb = 2048 if args.kind == "vanilla" else 4096
     s = lit.build_system(SimpleNamespace(exp_type=exp, run_max_steps=100000, white_back=True, N_max_objs=1, N_obj_code_length=128)).to(dev)
     s.train()
     s.trainer = SimpleNamespace(global_step=0, is_global_zero=rank == 0)
     opt = s.configure_optimizers()
+    torch.manual_seed(1234 + rank)                # ... and a different ray batch / different sampling draws per rank
     idx = torch.randperm(rays_o.shape[0], device=dev)[:Rb]
     batch = {"rays_o": rays_o[idx][None], "rays_d": rays_d[idx][None], "viewdirs": rays_d[idx][None],
              "target": torch.rand(1, Rb, 3, device=dev)}
