@@ -128,3 +128,30 @@ def test_product_synth_generators_match_oracle_copies(built_lib):
         assert list(a) == list(b)
         assert all(torch.equal(a[k], b[k]) for k in a)
     assert torch.equal(synth.sapien_camera(3), O.sapien_camera(3))
+
+
+@pytest.mark.parametrize("kind", ["vanilla", "autodecoder"])
+def test_training_gradients_golden(kind, golden_dir):
+    """The oracle's TRAINING path (randomized sampling with the stored draws, loss0 + loss1, torch autograd) against the
+    reference's own autograd (oracle/gen_golden_train.py asserted bit equality of the loss and all 48 / 83 gradients in the
+    build container): the GPU gradient tests check our kernels against exactly this autograd."""
+    g = np.load(os.path.join(golden_dir, "train_%s_sharp_R33.npz" % kind))
+    sd = O.make_state_dict(kind, 0, sharp=True)
+    assert abs(sum(v.double().abs().sum().item() for v in sd.values()) - float(g["sd_checksum"])) < 1e-6 * float(g["sd_checksum"])
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    rays = {k: _t(g[k]) for k in ("rays_o", "rays_d", "viewdirs")}
+    lat = O.code_library(p, torch.tensor([0]), torch.tensor([3])) if kind == "autodecoder" else None
+    out = O.nerf_forward(p, rays, True, True, 2.0, 6.0, latents=lat, t_rand=_t(g["t_rand"]), u=_t(g["u"]))
+    loss = O.img2mse(out[0][0], _t(g["target"])) + O.img2mse(out[1][0], _t(g["target"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-7
+    names = [str(n) for n in g["grad_names"]]
+    assert set(names) == {k for k, v in p.items() if v.grad is not None}
+    for n, want in zip(names, g["grad_abs_sums"]):               # every gradient, by its sum of magnitudes
+        got = p[n].grad.double().abs().sum().item()
+        assert abs(got - float(want)) <= 1e-5 * max(float(want), 1e-12), n
+    for key in g.files:                                          # a few whole gradients
+        if key.startswith("grad/"):
+            ref = _t(g[key])
+            got = p[key[5:]].grad
+            assert (got - ref).abs().max() <= 1e-5 * ref.abs().max().clamp_min(1e-12), key
