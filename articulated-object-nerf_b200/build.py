@@ -18,8 +18,9 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libaon_b200.so")
 SOURCES = ["aon_api.cu", "render_simt.cu", "render_tc.cu", "train_ops.cu", "gemm_tc.cu"]
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+FLAGS = CFLAGS + ["-shared"]
 
 
 def _digest() -> str:
@@ -35,19 +36,59 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def _compile_one(args):
+    nvcc, src, obj = args
+    cmd = [nvcc] + CFLAGS + ["-c", "-o", obj, src]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return src, " ".join(cmd), proc.returncode, proc.stdout
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """One nvcc -c per source file, in parallel (objects cached under csrc/_obj, keyed by a hash of the file, the headers
+    and the flags), then one link into libaon_b200.so."""
+    from concurrent.futures import ThreadPoolExecutor
     stamp = LIB + ".sha256"
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + proc.stdout)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout)
-    if proc.returncode != 0:
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    hdr = hashlib.sha256()
+    for n in sorted(os.listdir(CSRC)) + ["../../include/aon.h"]:
+        p = os.path.join(CSRC, n)
+        if os.path.isfile(p) and not n.endswith(".cu"):
+            hdr.update(n.encode() + open(p, "rb").read())
+    hdr.update(" ".join(CFLAGS).encode())
+    jobs, objs = [], []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        h = hashlib.sha256(hdr.digest() + open(src, "rb").read()).hexdigest()[:16]
+        obj = os.path.join(objdir, "%s.%s.o" % (s[:-3], h))
+        objs.append(obj)
+        if force or not os.path.exists(obj):
+            for old in os.listdir(objdir):
+                if old.startswith(s[:-3] + "."):
+                    os.remove(os.path.join(objdir, old))
+            jobs.append((nvcc, src, obj))
+    log = []
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        results = list(ex.map(_compile_one, jobs))
+    failed = False
+    for src, cmd, rc, out in results:
+        log.append(cmd + "\n" + out)
+        failed = failed or rc != 0
+    if not failed:
+        cmd = [nvcc, "-shared", "-o", LIB] + objs
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        log.append(" ".join(cmd) + "\n" + proc.stdout)
+        failed = proc.returncode != 0
+    text = "\n".join(log)
+    with open(os.path.join(HERE, "build.log"), "a" if jobs and not force else "w") as f:
+        f.write(text)
+    if verbose or failed:
+        sys.stderr.write(text)
+    if failed:
         raise RuntimeError("nvcc failed building libaon_b200.so (see build.log)")
     with open(stamp, "w") as f:
         f.write(dig)

@@ -4,9 +4,8 @@
 #include <stdarg.h>
 #include <string.h>
 
-#include <mutex>
-
 #include "aon_common.cuh"
+#include "sampling.cuh"
 
 namespace aon {
 
@@ -150,44 +149,18 @@ __global__ void gather_latents_kernel(const float* __restrict__ shape,
 }
 
 // ---- A1+A2 ray generation -------------------------------------------------------------------------
-struct Cam {
-  float m[12];
-};
 __global__ void raygen_kernel(int H, int W, float focal, Cam c, float* __restrict__ rays_o,
                               float* __restrict__ rays_d) {
   const int n = H * W;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-    const int row = p / W, col = p % W;
-    // datasets/ray_utils.py:86-88: [(x - W/2)/f, -(y - H/2)/f, -1]
-    const float dx = __fdiv_rn((float)col - 0.5f * (float)W, focal);
-    const float dy = -__fdiv_rn((float)row - 0.5f * (float)H, focal);
-    const float dz = -1.0f;
-    // ray_utils.py:133: d_world = dirs @ c2w[:, :3].T
-    float wx = fmaf(dz, c.m[2], fmaf(dy, c.m[1], dx * c.m[0]));
-    float wy = fmaf(dz, c.m[6], fmaf(dy, c.m[5], dx * c.m[4]));
-    float wz = fmaf(dz, c.m[10], fmaf(dy, c.m[9], dx * c.m[8]));
-    // ray_utils.py:146-147: in-place normalisation (rays_d aliases viewdirs)
-    const float nrm = sqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx)));
-    rays_d[3 * p + 0] = __fdiv_rn(wx, nrm);
-    rays_d[3 * p + 1] = __fdiv_rn(wy, nrm);
-    rays_d[3 * p + 2] = __fdiv_rn(wz, nrm);
-    rays_o[3 * p + 0] = c.m[3];
-    rays_o[3 * p + 1] = c.m[7];
-    rays_o[3 * p + 2] = c.m[11];
+    float o[3], d[3];
+    ray_from_camera(p, H, W, focal, c, o, d);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { rays_d[3 * p + k] = d[k]; rays_o[3 * p + k] = o[k]; }
   }
 }
 
 // ---- A3 coarse sampling -------------------------------------------------------------------------------
-// torch.linspace(0,1,n) (fp32, CPU and CUDA): i < n/2 ? step*i : fma(-step, n-1-i, 1), step = 1/(n-1).
-__device__ __forceinline__ float linspace01(int i, int n, float end) {
-  const float step = __fdiv_rn(end, (float)(n - 1));
-  return i < n / 2 ? __fmul_rn(step, (float)i) : fmaf(-step, (float)(n - 1 - i), end);
-}
-__device__ __forceinline__ float coarse_t(int i, int n, float near, float far) {
-  const float s = linspace01(i, n, 1.0f);
-  // helper.py:120: near * (1 - s) + far * s, three separately rounded fp32 ops
-  return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, s)), __fmul_rn(far, s));
-}
 __global__ void sample_along_rays_kernel(float near, float far, int n, const float* __restrict__ t_rand,
                                          int R, float* __restrict__ t_vals) {
   const long total = t_rand ? (long)R * n : n;
@@ -209,137 +182,63 @@ __global__ void sample_along_rays_kernel(float near, float far, int n, const flo
 }
 
 // ---- A7 hierarchical sampling ----------------------------------------------------------------------------
-// One warp per ray.  helper.py:203-252 + model.py:162-166.  The bracket search
-// (idx = #{cdf <= u}) is bit-equivalent to the reference's mask-max/min formulation
-// (oracle: sorted_piecewise_constant_pdf_bracket); the reference's full sort of the concatenated
-// [t_coarse | samples] is done as a rank sort (stable on ties), which is also correct for the
-// unsorted u of randomized training.
-constexpr int PDF_MAX_COARSE = 65;
-constexpr int PDF_MAX_FINE = 128;
+// One warp per ray (sampling.cuh: sample_pdf_ray; the fused image kernel runs the same function in-kernel).
 constexpr int PDF_WARPS = 8;
 
 __global__ void __launch_bounds__(PDF_WARPS * 32)
 sample_pdf_kernel(const float* __restrict__ t_coarse, long t_stride, const float* __restrict__ weights,
                   const float* __restrict__ u_in, long u_stride, int R, int nc, int nf,
                   float* __restrict__ t_fine) {
-  __shared__ float s_t[PDF_WARPS][PDF_MAX_COARSE + PDF_MAX_FINE + 3];
-  __shared__ float s_bins[PDF_WARPS][PDF_MAX_COARSE];
-  __shared__ float s_cdf[PDF_WARPS][PDF_MAX_COARSE];
+  __shared__ float s_scr[PDF_WARPS][PDF_SCRATCH_FLOATS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nb = nc - 1;  // bins = midpoints (64); interior weights = nb - 1 (63)
-  const int nw = nb - 1;
-  const int ntot = nc + nf;
-  for (long ray = (long)blockIdx.x * PDF_WARPS + warp; ray < R; ray += (long)gridDim.x * PDF_WARPS) {
-    float* st = s_t[warp];
-    float* sb = s_bins[warp];
-    float* sc = s_cdf[warp];
-    const float* tc = t_coarse + ray * t_stride;
-    const float* w = weights + ray * (long)nc;
-    for (int i = lane; i < nc; i += 32) st[i] = tc[i];
-    __syncwarp();
-    for (int i = lane; i < nb; i += 32) sb[i] = __fmul_rn(0.5f, __fadd_rn(st[i + 1], st[i]));
-    // weight sum over the interior weights w[1 .. nc-2]
-    float part = 0.f;
-    for (int i = lane; i < nw; i += 32) part += w[1 + i];
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    const float wsum0 = part;
-    const float padding = fmaxf(0.f, __fsub_rn(1e-5f, wsum0));
-    const float padw = __fdiv_rn(padding, (float)nw);
-    const float wsum = __fadd_rn(wsum0, padding);
-    // cdf[0]=0, cdf[k]=min(1, cumsum(pdf)[k-1]) for k=1..nw-1, cdf[nw]=1   (nw+1 = nb entries)
-    // pdf in parallel, then the sequential fp32 cumsum of torch.cumsum (CPU) by lane 0 (62 adds).
-    for (int k = lane; k < nw - 1; k += 32) sc[k + 1] = __fdiv_rn(__fadd_rn(w[1 + k], padw), wsum);
-    __syncwarp();
-    if (lane == 0) {
-      float c = 0.f;
-      sc[0] = 0.f;
-      for (int k = 0; k < nw - 1; ++k) {
-        c = __fadd_rn(c, sc[k + 1]);
-        sc[k + 1] = fminf(1.0f, c);
-      }
-      sc[nw] = 1.0f;
-    }
-    __syncwarp();
-    for (int j = lane; j < nf; j += 32) {
-      float u;
-      if (u_in) {
-        u = u_in[ray * u_stride + j];
-      } else {
-        // helper.py:229: linspace(0, 1 - 2^-32, nf); the end point rounds to 1.0f
-        u = linspace01(j, nf, 1.0f);
-      }
-      // idx = #{k : cdf[k] <= u}; cdf is non-decreasing -> binary search
-      int lo = 0, hi = nb;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (sc[mid] <= u) lo = mid + 1; else hi = mid;
-      }
-      const int i0 = max(lo - 1, 0), i1 = min(lo, nb - 1);
-      const float c0 = sc[i0], c1 = sc[i1], b0 = sb[i0], b1 = sb[i1];
-      float t = __fdiv_rn(__fsub_rn(u, c0), __fsub_rn(c1, c0));
-      if (isnan(t)) t = 0.f;               // nan_to_num(., 0): 0/0 -> 0
-      else if (isinf(t)) t = t > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
-      t = fminf(fmaxf(t, 0.f), 1.f);
-      st[nc + j] = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
-    }
-    __syncwarp();
-    // The reference sorts cat[t_coarse, samples] (helper.py:250).  t_coarse is sorted; if the samples came out
-    // non-decreasing too (always, up to rounding, for the deterministic u table) the stable sort is a merge:
-    //   rank(coarse i) = i + #{samples < t_i},  rank(sample j) = #{coarse <= s_j} + j      (two binary searches)
-    // otherwise (unsorted random u, or a 1-ulp inversion at a bracket boundary) fall back to a rank sort.
-    float* out = t_fine + ray * (long)ntot;
-    bool sorted = true;
-    for (int j = lane; j < nf - 1; j += 32) sorted = sorted && (st[nc + j] <= st[nc + j + 1]);
-    for (int i = lane; i < nc - 1; i += 32) sorted = sorted && (st[i] <= st[i + 1]);
-    sorted = __all_sync(0xffffffffu, sorted);
-    if (sorted) {
-      for (int i = lane; i < ntot; i += 32) {
-        const float v = st[i];
-        int lo = 0, hi, rank;
-        if (i < nc) {          // first sample index with s >= v
-          hi = nf;
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (st[nc + mid] < v) lo = mid + 1; else hi = mid; }
-          rank = i + lo;
-        } else {               // first coarse index with t > v
-          hi = nc;
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (st[mid] <= v) lo = mid + 1; else hi = mid; }
-          rank = (i - nc) + lo;
-        }
-        out[rank] = v;
-      }
-    } else {
-      for (int i = lane; i < ntot; i += 32) {
-        const float v = st[i];
-        int rank = 0;
-        for (int j = 0; j < ntot; ++j) {
-          const float x = st[j];
-          rank += (x < v) || (x == v && j < i);
-        }
-        out[rank] = v;
-      }
-    }
-    __syncwarp();
+  for (long ray = (long)blockIdx.x * PDF_WARPS + warp; ray < R; ray += (long)gridDim.x * PDF_WARPS)
+    sample_pdf_ray<false>(t_coarse + ray * t_stride, weights + ray * (long)nc, u_in ? u_in + ray * u_stride : nullptr, nc, nf,
+                          s_scr[warp], t_fine + ray * (long)(nc + nf), lane);
+}
+
+// rays of pixels [p0, p0 + n) of an H x W view (tail of a fused image render that takes the three-launch path)
+__global__ void raygen_range_kernel(int H, int W, float focal, Cam c, long p0, int n, float* __restrict__ rays_o,
+                                    float* __restrict__ rays_d) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float o[3], d[3];
+    ray_from_camera(p0 + i, H, W, focal, c, o, d);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { rays_d[3 * (size_t)i + k] = d[k]; rays_o[3 * (size_t)i + k] = o[k]; }
   }
 }
 
-__global__ void interleave5_kernel(const float* __restrict__ planes, int R, float* __restrict__ out) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= R) return;
-  out[5 * (size_t)r + 0] = planes[3 * (size_t)r + 0];
-  out[5 * (size_t)r + 1] = planes[3 * (size_t)r + 1];
-  out[5 * (size_t)r + 2] = planes[3 * (size_t)r + 2];
-  out[5 * (size_t)r + 3] = planes[(size_t)3 * R + r];
-  out[5 * (size_t)r + 4] = planes[(size_t)4 * R + r];
-}
-
-// scratch arena for aon_render_image_host (per process, grown on demand, guarded by a mutex)
-struct Arena {
-  std::mutex mu;
-  char* base = nullptr;
-  size_t cap = 0;
-  int device = -1;
+// ---- workspace layout (aon_workspace_bytes) --------------------------------------------------------------------
+// [slot mask 256 B | coarse t table 512 B | fused scratch slots | tail: rays 6 | w0 65 | t1 193 | coarse out 5 | seg 193 x 4
+//  (floats per tail ray) | host staging: rays 9 + out 5 + coarse out 5 floats per ray]
+struct WsLayout {
+  size_t mask, t0, slots, tail_rays, tail_w0, tail_t1, tail_c5, tail_seg, seg_bytes, stage, total;
+  long tail_cap;   // rays the three-launch path can take
 };
-static Arena g_arena;
+static size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+static bool ws_layout(int precision, long R, WsLayout* L) {
+  const bool tc = precision >= AON_PREC_TC_F16X3 && precision <= AON_PREC_TC_BF16;
+  if (!tc && precision != AON_PREC_FP32) return false;
+  if (R < 0) return false;
+  size_t off = 0;
+  L->mask = off; off += 256;
+  L->t0 = off; off += 512;
+  L->slots = off;
+  if (tc) off += up256((size_t)MAX_SLOTS * 128 * (N_COARSE + N_TOTAL) * 4);
+  // tensor-core modes: only the last partial wave (< MAX_SLOTS / 2 CTA pairs) or a batch smaller than one wave takes the
+  // three-launch path; fp32: every ray does
+  const long cap = tc ? (R < MAX_SLOTS / 2 * 256 ? R : MAX_SLOTS / 2 * 256) : R;
+  L->tail_cap = cap;
+  L->tail_rays = off; off += up256((size_t)cap * 6 * 4);
+  L->tail_w0 = off; off += up256((size_t)cap * N_COARSE * 4);
+  L->tail_t1 = off; off += up256((size_t)cap * N_TOTAL * 4);
+  L->tail_c5 = off; off += up256((size_t)cap * 5 * 4);
+  L->tail_seg = off;
+  L->seg_bytes = tc ? up256(seg_bytes_tc((int)R, N_TOTAL)) : 0;
+  off += L->seg_bytes;
+  L->stage = off; off += up256((size_t)R * 19 * 4);
+  L->total = off;
+  return true;
+}
 
 size_t folded_floats_tc(int kind);                                                            // render_tc.cu
 int fold_stages_tc(int kind, int precision, const PackedLayout& L, float* folded, cudaStream_t st);  // render_tc.cu
@@ -472,65 +371,148 @@ int aon_sample_pdf(const float* t_coarse, long t_stride, const float* weights, c
   return AON_OK;
 }
 
+size_t aon_workspace_bytes(int precision, int R) {
+  WsLayout L;
+  return ws_layout(precision, R, &L) ? L.total : 0;
+}
+
+// Three-launch path (coarse level, sample_pdf, fine level) over n rays given as device arrays; t0 as in aon_render_rays.
+static int render_unfused(int kind, int precision, const void* pc, const void* pf, const float* fc, const float* ff,
+                          const float* o, const float* d, const float* v, const float* t0, long t0_stride, const float* u,
+                          long u_stride, int n, int white_bkgd, float* out5, float* coarse_out5, char* ws, const WsLayout& L,
+                          const AonRenderOpts* opts, cudaStream_t st) {
+  float* w0 = (float*)(ws + L.tail_w0);
+  float* t1 = (float*)(ws + L.tail_t1);
+  float* c5 = coarse_out5 ? coarse_out5 : (float*)(ws + L.tail_c5);
+  void* seg = ws + L.tail_seg;
+  int rc = render_level_any(kind, precision, pc, fc, o, d, v, t0, t0_stride, n, N_COARSE, white_bkgd, nullptr, nullptr,
+                            nullptr, c5, w0, seg, L.seg_bytes, opts, st);
+  if (rc != AON_OK) return rc;
+  if ((rc = aon_sample_pdf(t0, t0_stride, w0, u, u_stride, n, N_COARSE, N_FINE, t1, (aon_stream_t)st)) != AON_OK) return rc;
+  return render_level_any(kind, precision, pf, ff, o, d, v, t1, N_TOTAL, n, N_TOTAL, white_bkgd, nullptr, nullptr, nullptr,
+                          out5, nullptr, seg, L.seg_bytes, opts, st);
+}
+
+// common body of aon_render_rays (cam == nullptr) and aon_render_image (rays_* == nullptr)
+static int render_all(int kind, int precision, const void* pc, const void* pf, const float* fc, const float* ff,
+                      const float* rays_o, const float* rays_d, const float* viewdirs, const Cam* cam, int H, int W,
+                      float focal, long ray0, const float* t_coarse, const float* u, int R, float near, float far,
+                      int white_bkgd, float* out, float* coarse_out, void* workspace, size_t workspace_bytes,
+                      const AonRenderOpts* opts, cudaStream_t st, const char* who) {
+  AON_REQUIRE(kind == AON_KIND_VANILLA || kind == AON_KIND_AUTODECODER, "%s: bad kind %d", who, kind);
+  AON_REQUIRE(pc && pf && out, "%s: null pointer", who);
+  AON_REQUIRE(kind == AON_KIND_VANILLA || (fc && ff), "%s: auto-decoder needs the folded biases of aon_fold_latents()", who);
+  AON_REQUIRE(R >= 0, "%s: R must be non-negative", who);
+  AON_REQUIRE((((uintptr_t)pc | (uintptr_t)pf) & 255) == 0, "%s: packed buffers must be 256-byte aligned", who);
+  if (R == 0) return AON_OK;
+  WsLayout L;
+  if (!ws_layout(precision, R, &L)) { set_error("%s: bad precision %d", who, precision); return AON_E_ARG; }
+  AON_REQUIRE(workspace && ((uintptr_t)workspace & 255) == 0, "%s: workspace must be a 256-byte aligned device buffer", who);
+  if (workspace_bytes < L.total) {
+    set_error("%s: workspace too small: %zu < aon_workspace_bytes() = %zu", who, workspace_bytes, L.total);
+    return AON_E_SIZE;
+  }
+  char* ws = (char*)workspace;
+  int rc;
+  const float* t0 = t_coarse;
+  long t0_stride = N_COARSE;
+  if (t0 == nullptr) {
+    float* tab = (float*)(ws + L.t0);
+    if ((rc = aon_sample_along_rays(near, far, N_COARSE, nullptr, R, tab, (aon_stream_t)st)) != AON_OK) return rc;
+    t0 = tab;
+    t0_stride = 0;
+  }
+  const long u_stride = u ? N_FINE : 0;
+  const bool tc = precision != AON_PREC_FP32;
+  int R_main = 0, nsc = 1, nsf = 1;
+  if (tc && !(opts && opts->no_fuse)) {
+    int dev = 0, sms = 148;
+    AON_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    R_main = (opts && opts->no_tail_split) ? R : tail_split_tc(R, sms, &nsc, &nsf);
+    if (R - R_main > L.tail_cap) R_main = R;
+  }
+  if (R_main > 0) {
+    AON_CUDA_CHECK(cudaMemsetAsync(ws + L.mask, 0, 256, st));
+    rc = render_fused_tc(kind, precision, pc, pf, fc, ff, rays_o, rays_d, viewdirs, cam, H, W, focal, ray0, t0, t0_stride, u,
+                         u_stride, R_main, N_COARSE, N_TOTAL, white_bkgd, out, coarse_out, (float*)(ws + L.slots),
+                         (unsigned*)(ws + L.mask), MAX_SLOTS, opts, st);
+    if (rc != AON_OK) return rc;
+  }
+  const int n = R - R_main;
+  if (n == 0) return AON_OK;
+  const float *o, *d, *v;
+  if (cam) {
+    float* ro = (float*)(ws + L.tail_rays);
+    float* rd = ro + 3 * (size_t)n;
+    raygen_range_kernel<<<(n + 255) / 256, 256, 0, st>>>(H, W, focal, *cam, ray0 + R_main, n, ro, rd);
+    AON_LAUNCH_CHECK();
+    o = ro; d = rd; v = rd;
+  } else {
+    o = rays_o + 3 * (size_t)R_main; d = rays_d + 3 * (size_t)R_main; v = viewdirs + 3 * (size_t)R_main;
+  }
+  return render_unfused(kind, precision, pc, pf, fc, ff, o, d, v, t0 + (size_t)R_main * t0_stride, t0_stride,
+                        u ? u + (size_t)R_main * u_stride : nullptr, u_stride, n, white_bkgd, out + 5 * (size_t)R_main,
+                        coarse_out ? coarse_out + 5 * (size_t)R_main : nullptr, ws, L, opts, st);
+}
+
+int aon_render_rays(int kind, int precision, const void* packed_coarse, const void* packed_fine,
+                    const float* folded_coarse, const float* folded_fine, const float* rays_o,
+                    const float* rays_d, const float* viewdirs, const float* t_coarse, const float* u,
+                    int R, float near, float far, int white_bkgd, float* out, float* coarse_out,
+                    void* workspace, size_t workspace_bytes, const AonRenderOpts* opts,
+                    aon_stream_t stream) {
+  AON_REQUIRE(R == 0 || (rays_o && rays_d && viewdirs), "aon_render_rays: null ray pointer");
+  return render_all(kind, precision, packed_coarse, packed_fine, folded_coarse, folded_fine, rays_o, rays_d, viewdirs,
+                    nullptr, 0, 0, 0.f, 0, t_coarse, u, R, near, far, white_bkgd, out, coarse_out, workspace,
+                    workspace_bytes, opts, (cudaStream_t)stream, "aon_render_rays");
+}
+
+int aon_render_image(int kind, int precision, const void* packed_coarse, const void* packed_fine,
+                     const float* folded_coarse, const float* folded_fine, const float* c2w_host,
+                     float focal, int H, int W, long ray0, int R, float near, float far,
+                     int white_bkgd, float* out, float* coarse_out, void* workspace,
+                     size_t workspace_bytes, const AonRenderOpts* opts, aon_stream_t stream) {
+  AON_REQUIRE(c2w_host && H > 0 && W > 0 && focal > 0.f, "aon_render_image: bad camera");
+  AON_REQUIRE(ray0 >= 0 && R >= 0 && ray0 + R <= (long)H * W, "aon_render_image: pixel range [%ld, %ld) outside the %d x %d image",
+              ray0, ray0 + R, H, W);
+  Cam c;
+  memcpy(c.m, c2w_host, sizeof(c.m));
+  return render_all(kind, precision, packed_coarse, packed_fine, folded_coarse, folded_fine, nullptr, nullptr, nullptr, &c,
+                    H, W, focal, ray0, nullptr, nullptr, R, near, far, white_bkgd, out, coarse_out, workspace,
+                    workspace_bytes, opts, (cudaStream_t)stream, "aon_render_image");
+}
+
 int aon_render_image_host(int kind, int precision, const void* packed_coarse, const void* packed_fine,
                           const float* folded_coarse, const float* folded_fine,
                           const float* rays_o_host, const float* rays_d_host,
                           const float* viewdirs_host, int R, float near, float far, int white_bkgd,
-                          float* out_host, float* coarse_out_host, aon_stream_t stream) {
+                          float* out_host, float* coarse_out_host, void* workspace, size_t workspace_bytes,
+                          const AonRenderOpts* opts, aon_stream_t stream) {
   AON_REQUIRE(packed_coarse && packed_fine && rays_o_host && rays_d_host && viewdirs_host && out_host,
               "aon_render_image_host: null pointer");
   AON_REQUIRE(R > 0, "aon_render_image_host: R must be positive");
   cudaStream_t st = (cudaStream_t)stream;
-  const int S0 = 65, NF = 128, S1 = S0 + NF;
-  // arena: rays 9R | t0 S0 | w0 R*S0 | t1 R*S1 | out0 5R | out1 5R   (floats)
-  const size_t nfl = (size_t)R * (9 + S0 + S1 + 10) + 256;
-  int dev = 0;
-  AON_CUDA_CHECK(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lock(g_arena.mu);
-  if (g_arena.device != dev || g_arena.cap < nfl * 4) {
-    if (g_arena.base) cudaFree(g_arena.base);
-    g_arena.base = nullptr;
-    g_arena.cap = 0;
-    AON_CUDA_CHECK(cudaMalloc(&g_arena.base, nfl * 4));
-    g_arena.cap = nfl * 4;
-    g_arena.device = dev;
-  }
-  float* f = (float*)g_arena.base;
+  WsLayout L;
+  if (!ws_layout(precision, R, &L)) { set_error("aon_render_image_host: bad precision %d", precision); return AON_E_ARG; }
+  AON_REQUIRE(workspace && workspace_bytes >= L.total, "aon_render_image_host: workspace missing or smaller than aon_workspace_bytes()");
+  float* f = (float*)((char*)workspace + L.stage);
   float* d_o = f;               f += (size_t)3 * R;
   float* d_d = f;               f += (size_t)3 * R;
   float* d_v = f;               f += (size_t)3 * R;
-  float* d_t0 = f;              f += 256;
-  float* d_w0 = f;              f += (size_t)R * S0;
-  float* d_t1 = f;              f += (size_t)R * S1;
-  float* d_out0 = f;            f += (size_t)5 * R;
-  float* d_out1 = f;
+  float* d_out = f;             f += (size_t)5 * R;
+  float* d_out0 = f;
   const size_t rb = (size_t)3 * R * 4;
   AON_CUDA_CHECK(cudaMemcpyAsync(d_o, rays_o_host, rb, cudaMemcpyHostToDevice, st));
   AON_CUDA_CHECK(cudaMemcpyAsync(d_d, rays_d_host, rb, cudaMemcpyHostToDevice, st));
   AON_CUDA_CHECK(cudaMemcpyAsync(d_v, viewdirs_host, rb, cudaMemcpyHostToDevice, st));
-  int rc;
-  if ((rc = aon_sample_along_rays(near, far, S0, nullptr, R, d_t0, stream)) != AON_OK) return rc;
-  // outputs are packed [R,5] on the host side; on the device rgb [R,3] | acc [R] | depth [R]
-  if ((rc = aon_render_level(kind, precision, packed_coarse, folded_coarse, d_o, d_d, d_v, d_t0, 0, R, S0,
-                             white_bkgd, d_out0, d_out0 + (size_t)3 * R, d_out0 + (size_t)4 * R, d_w0,
-                             stream)) != AON_OK)
-    return rc;
-  if ((rc = aon_sample_pdf(d_t0, 0, d_w0, nullptr, 0, R, S0, NF, d_t1, stream)) != AON_OK) return rc;
-  if ((rc = aon_render_level(kind, precision, packed_fine, folded_fine, d_o, d_d, d_v, d_t1, S1, R, S1,
-                             white_bkgd, d_out1, d_out1 + (size_t)3 * R, d_out1 + (size_t)4 * R, nullptr,
-                             stream)) != AON_OK)
-    return rc;
-  // interleave (rgb | acc | depth) planes into the [R,5] host layout, then one contiguous D2H each
-  float* d_pack = d_t1;  // t1 is dead after the fine level
-  interleave5_kernel<<<(R + 255) / 256, 256, 0, st>>>(d_out1, R, d_pack);
-  AON_LAUNCH_CHECK();
-  AON_CUDA_CHECK(cudaMemcpyAsync(out_host, d_pack, (size_t)R * 20, cudaMemcpyDeviceToHost, st));
-  if (coarse_out_host) {
-    interleave5_kernel<<<(R + 255) / 256, 256, 0, st>>>(d_out0, R, d_pack + (size_t)5 * R);
-    AON_LAUNCH_CHECK();
-    AON_CUDA_CHECK(cudaMemcpyAsync(coarse_out_host, d_pack + (size_t)5 * R, (size_t)R * 20,
-                                   cudaMemcpyDeviceToHost, st));
-  }
+  int rc = aon_render_rays(kind, precision, packed_coarse, packed_fine, folded_coarse, folded_fine, d_o, d_d, d_v, nullptr,
+                           nullptr, R, near, far, white_bkgd, d_out, coarse_out_host ? d_out0 : nullptr, workspace,
+                           workspace_bytes, opts, stream);
+  if (rc != AON_OK) return rc;
+  AON_CUDA_CHECK(cudaMemcpyAsync(out_host, d_out, (size_t)R * 20, cudaMemcpyDeviceToHost, st));
+  if (coarse_out_host)
+    AON_CUDA_CHECK(cudaMemcpyAsync(coarse_out_host, d_out0, (size_t)R * 20, cudaMemcpyDeviceToHost, st));
   AON_CUDA_CHECK(cudaStreamSynchronize(st));
   return AON_OK;
 }

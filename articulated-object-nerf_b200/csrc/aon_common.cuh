@@ -50,6 +50,26 @@ PackedLayout layout_fp32(int kind);
 // tensor-core packing (defined in render_tc.cu)
 PackedLayout layout_tc(int kind, int precision);
 
+// ---- render entry points shared between the translation units ----------------------------------------------------
+struct Cam;   // sampling.cuh
+constexpr int MAX_SLOTS = 160;   // per-CTA scratch slots of the fused image kernel (>= SM count of any sm_100 part)
+constexpr int N_COARSE = 65, N_FINE = 128, N_TOTAL = N_COARSE + N_FINE;   // samples per ray (model.py:128-129: 64 + 1, 128)
+int render_level_tc(int kind, int precision, const void* packed, const float* folded, const float* rays_o,
+                    const float* rays_d, const float* viewdirs, const float* t_vals, long t_stride, int R, int S,
+                    int white_bkgd, float* comp_rgb, float* acc, float* depth, float* out5, float* weights, void* workspace,
+                    size_t workspace_bytes, const AonRenderOpts* opts, cudaStream_t st);
+int render_level_any(int kind, int precision, const void* packed, const float* folded, const float* rays_o,
+                     const float* rays_d, const float* viewdirs, const float* t_vals, long t_stride, int R, int S,
+                     int white_bkgd, float* comp_rgb, float* acc, float* depth, float* out5, float* weights,
+                     void* workspace, size_t workspace_bytes, const AonRenderOpts* opts, cudaStream_t st);
+int render_fused_tc(int kind, int precision, const void* packed_c, const void* packed_f, const float* folded_c,
+                    const float* folded_f, const float* rays_o, const float* rays_d, const float* viewdirs, const Cam* cam,
+                    int H, int W, float focal, long ray0, const float* t0, long t0_stride, const float* u, long u_stride,
+                    int R, int S0, int S1, int white_bkgd, float* out5, float* coarse_out5, float* slots, unsigned* slot_mask,
+                    int n_slots, const AonRenderOpts* opts, cudaStream_t st);
+size_t seg_bytes_tc(int R, int S);
+int tail_split_tc(int R, int sms, int* n_seg_coarse, int* n_seg_fine);
+
 // ---- device math -------------------------------------------------------------------------------
 // The reference encodes the cosine half as sin(fl32(2^k x) + fl32(pi/2)) (helper.py:139); 2^k x is
 // exact in fp32, the +pi/2 is a rounded fp32 add.  __fadd_rn keeps the compiler from contracting.

@@ -31,6 +31,7 @@ struct SimtParams {
   float* comp_rgb;
   float* acc;
   float* depth;
+  float* out5;     // interleaved [R,5] = (r, g, b, acc, depth); when set, the three planes above are not written
   float* weights;
 };
 
@@ -297,15 +298,19 @@ __global__ void __launch_bounds__(NT, 1) render_simt_kernel(const SimtParams p) 
       const float bg = __fsub_rn(1.0f, cacc);
       cr += bg; cg += bg; cb += bg;
     }
-    p.comp_rgb[3 * ray + 0] = cr; p.comp_rgb[3 * ray + 1] = cg; p.comp_rgb[3 * ray + 2] = cb;
-    p.acc[ray] = cacc;
-    p.depth[ray] = cdepth;
+    if (p.out5 != nullptr) {
+      p.out5[5 * ray + 0] = cr; p.out5[5 * ray + 1] = cg; p.out5[5 * ray + 2] = cb; p.out5[5 * ray + 3] = cacc; p.out5[5 * ray + 4] = cdepth;
+    } else {
+      p.comp_rgb[3 * ray + 0] = cr; p.comp_rgb[3 * ray + 1] = cg; p.comp_rgb[3 * ray + 2] = cb;
+      p.acc[ray] = cacc;
+      p.depth[ray] = cdepth;
+    }
   }
 }
 
 int render_level_simt(int kind, const void* packed, const float* folded, const float* rays_o,
                       const float* rays_d, const float* viewdirs, const float* t_vals, long t_stride,
-                      int R, int S, int white_bkgd, float* comp_rgb, float* acc, float* depth,
+                      int R, int S, int white_bkgd, float* comp_rgb, float* acc, float* depth, float* out5,
                       float* weights, cudaStream_t st) {
   SimtParams p;
   p.packed = (const char*)packed;
@@ -314,7 +319,7 @@ int render_level_simt(int kind, const void* packed, const float* folded, const f
   p.rays_o = rays_o; p.rays_d = rays_d; p.viewdirs = viewdirs;
   p.t_vals = t_vals; p.t_stride = t_stride;
   p.R = R; p.S = S; p.white_bkgd = white_bkgd;
-  p.comp_rgb = comp_rgb; p.acc = acc; p.depth = depth; p.weights = weights;
+  p.comp_rgb = comp_rgb; p.acc = acc; p.depth = depth; p.out5 = out5; p.weights = weights;
   const int grid = (R + RT - 1) / RT;
   const size_t smem = sizeof(Smem);
   if (kind == AON_KIND_VANILLA) {
@@ -330,22 +335,30 @@ int render_level_simt(int kind, const void* packed, const float* folded, const f
   return AON_OK;
 }
 
+// One level in the precision's kernel; out5 (interleaved) or the three planes receive the composite.
+int render_level_any(int kind, int precision, const void* packed, const float* folded, const float* rays_o,
+                     const float* rays_d, const float* viewdirs, const float* t_vals, long t_stride, int R, int S,
+                     int white_bkgd, float* comp_rgb, float* acc, float* depth, float* out5, float* weights,
+                     void* workspace, size_t workspace_bytes, const AonRenderOpts* opts, cudaStream_t st) {
+  if (precision == AON_PREC_FP32)
+    return render_level_simt(kind, packed, folded, rays_o, rays_d, viewdirs, t_vals, t_stride, R, S, white_bkgd, comp_rgb,
+                             acc, depth, out5, weights, st);
+  if (precision >= AON_PREC_TC_F16X3 && precision <= AON_PREC_TC_BF16)
+    return render_level_tc(kind, precision, packed, folded, rays_o, rays_d, viewdirs, t_vals, t_stride, R, S, white_bkgd,
+                           comp_rgb, acc, depth, out5, weights, workspace, workspace_bytes, opts, st);
+  set_error("bad precision %d", precision);
+  return AON_E_ARG;
+}
+
 }  // namespace aon
 
 using namespace aon;
 
-namespace aon {
-int render_level_tc(int kind, int precision, const void* packed, const float* folded, const float* rays_o,
-                    const float* rays_d, const float* viewdirs, const float* t_vals, long t_stride, int R,
-                    int S, int white_bkgd, float* comp_rgb, float* acc, float* depth, float* weights,
-                    cudaStream_t st);
-}
-
 extern "C" int aon_render_level(int kind, int precision, const void* packed, const float* folded,
                                 const float* rays_o, const float* rays_d, const float* viewdirs,
                                 const float* t_vals, long t_stride, int R, int S, int white_bkgd,
-                                float* comp_rgb, float* acc, float* depth, float* weights,
-                                aon_stream_t stream) {
+                                float* comp_rgb, float* acc, float* depth, float* weights, void* workspace,
+                                size_t workspace_bytes, const AonRenderOpts* opts, aon_stream_t stream) {
   AON_REQUIRE(kind == AON_KIND_VANILLA || kind == AON_KIND_AUTODECODER, "bad kind %d", kind);
   AON_REQUIRE(packed && rays_o && rays_d && viewdirs && t_vals && comp_rgb && acc && depth,
               "aon_render_level: null pointer");
@@ -354,14 +367,9 @@ extern "C" int aon_render_level(int kind, int precision, const void* packed, con
   AON_REQUIRE(R >= 0 && S >= 1, "aon_render_level: bad sizes R=%d S=%d", R, S);
   AON_REQUIRE(t_stride == 0 || t_stride >= S, "aon_render_level: bad t_stride %ld", t_stride);
   AON_REQUIRE(((uintptr_t)packed & 255) == 0, "packed buffer must be 256-byte aligned");
+  AON_REQUIRE(workspace == nullptr || ((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   if (R == 0) return AON_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (precision == AON_PREC_FP32)
-    return render_level_simt(kind, packed, folded, rays_o, rays_d, viewdirs, t_vals, t_stride, R, S,
-                             white_bkgd, comp_rgb, acc, depth, weights, st);
-  if (precision >= AON_PREC_TC_F16X3 && precision <= AON_PREC_TC_BF16)
-    return render_level_tc(kind, precision, packed, folded, rays_o, rays_d, viewdirs, t_vals, t_stride, R,
-                           S, white_bkgd, comp_rgb, acc, depth, weights, st);
-  set_error("bad precision %d", precision);
-  return AON_E_ARG;
+  return render_level_any(kind, precision, packed, folded, rays_o, rays_d, viewdirs, t_vals, t_stride, R, S, white_bkgd,
+                          comp_rgb, acc, depth, nullptr, weights, workspace, workspace ? workspace_bytes : 0, opts,
+                          (cudaStream_t)stream);
 }

@@ -35,6 +35,7 @@
 #include <string.h>
 
 #include "aon_common.cuh"
+#include "sampling.cuh"
 #include "tc_ptx.cuh"
 
 namespace aon {
@@ -345,30 +346,49 @@ struct SmemPlan {
 struct TcParams {
   Program prog;
   PackedLayout L;
-  const char* packed;
-  const float* folded;
+  // per level: the fused image kernel walks level 0 (coarse) then level 1 (fine); a classic launch has level 0 only
+  const char* packed[2];
+  const float* folded[2];
+  int S_level[2];
+  int n_levels;
+  // ray source: arrays [R,3], or a pinhole camera (cam_on; pixel index = ray0 + ray; sampling.cuh ray_from_camera)
   const float* rays_o;
   const float* rays_d;
   const float* viewdirs;
+  int cam_on, img_H, img_W;
+  float focal;
+  Cam cam;
+  long ray0;
+  // level-0 sample positions: shared table [S] (t_stride 0) or [R,S]
   const float* t_vals;
   long t_stride;
-  int R, S, white_bkgd;
-  int seg_len, n_seg;  // samples per CTA (blockIdx.y = segment) and number of segments; n_seg > 1 -> partial results
-  float* partial;      // [n_seg][R][8] = (T, r, g, b, depth, acc, -, -) of each segment, folded by combine_segments_kernel
+  // fused kernel only: inverse-cdf draws [R,nf] or nullptr (deterministic table), and the per-CTA scratch slots
+  // ([n_slots][128 x (S0 + S1)] floats: coarse weights, then fine t) handed out through a bit mask
+  const float* u;
+  long u_stride;
+  float* slots;
+  unsigned* slot_mask;
+  int n_slots;
+  int R, white_bkgd;
+  int seg_len, n_seg;  // classic launch: samples per CTA (blockIdx.y = segment) and number of segments
+  float4* seg_samples; // n_seg > 1: [R][S] (alpha, r, g, b) per sample, composited in order by composite_samples_kernel
+  // outputs of the last level: planes (comp_rgb [R,3], acc [R], depth [R]) or interleaved out5 [R,5]
   float* comp_rgb;
   float* acc;
   float* depth;
-  float* weights;
+  float* out5;
+  float* weights;      // classic launch, n_seg == 1: [R,S] compositing weights (optional)
+  float* coarse_out5;  // fused kernel: [R,5] of level 0 (optional)
   float* dbg;        // optional [n_units][128][256] pre-activation dump of tile 0 / sample 0
   int* err_flag;     // optional: set to a non-zero code when a barrier wait times out
   long long* tl;     // optional timeline [3 roles][4 samples][MAX_UNITS][4 events] of SM clocks, CTA 0 only
 };
 
-// barrier slots (8 bytes each) inside the BARS region
+// barrier slots (8 bytes each) inside the BARS region; the last two words hold the MMA issue ticket and the scratch slot
 constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_DFULL = 2 * MAX_STAGES, BAR_DEMPTY = BAR_DFULL + 2,
               BAR_CHUNK = BAR_DEMPTY + 2, BAR_EFREE = BAR_CHUNK + NUM_CHUNK_IDS, BAR_XW = BAR_EFREE + 1,
-              BAR_TMEM = BAR_XW + 2;
-static_assert((BAR_TMEM + 1) * 8 <= 384, "barrier region too small");
+              BAR_TMEM = BAR_XW + 2, WORD_TICKET = 2 * (BAR_TMEM + 1), WORD_SLOT = WORD_TICKET + 1;
+static_assert((WORD_SLOT + 1) * 4 <= 384, "barrier region too small");
 
 __device__ __forceinline__ void wait_slow(uint32_t bar, uint32_t parity, int* err_flag, int code) {
   const long long t0 = clock64();
@@ -394,6 +414,23 @@ __device__ __forceinline__ void spin_bar(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Issue ticket of the two MMA issuer threads: the number of weight stages whose MMAs have been ISSUED so far.  The thread
+// that owns stage n does all its waiting first (accumulator drained, operand chunk published, weights landed), then
+// spins until the ticket equals n, issues the stage's MMAs and passes the ticket on -- after issue, not after completion.
+// tcgen05.mma instructions execute in the order they enter the tensor core's queue, so every accumulator sees its K
+// steps in program order: results are bit-reproducible from run to run and independent of how rays are grouped into
+// tiles.  The hand-over costs a shared-memory store + load (tens of cycles) per stage against ~385 cycles of MMA
+// execution per stage.
+__device__ __forceinline__ void ticket_wait(uint32_t addr, uint32_t want) {
+  uint32_t v;
+  do {
+    asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  } while (v != want);
+}
+__device__ __forceinline__ void ticket_set(uint32_t addr, uint32_t v) {
+  asm volatile("st.volatile.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 template <bool X3, bool BF16>
 __device__ __forceinline__ void split16(float v, uint16_t& hi, uint16_t& lo) {
   if (BF16) {
@@ -416,38 +453,26 @@ __device__ __forceinline__ void put16(unsigned char* base, int lo_delta, int row
   if (X3) *reinterpret_cast<uint16_t*>(p + lo_delta) = lo;
 }
 
-// pos_enc (helper.py:136-140) of NR points (rows row + 32 r) into an operand region of NK columns:
+// pos_enc (helper.py:136-140) of one point (row `row`) into an operand region of NK columns:
 // [x y z | sin(2^f v_d) f-major | sin(2^f v_d + pi/2) f-major | zero padding]
-constexpr int ENC_ROWS = 1;   // rows per encoder thread (four encoder warps cover the 128-row tile)
 template <int L, int NK, bool X3, bool BF16>
-__device__ __forceinline__ void encode_store(unsigned char* base, int lo_delta, int row, const float (&x)[ENC_ROWS][3]) {
+__device__ __forceinline__ void encode_store(unsigned char* base, int lo_delta, int row, const float (&x)[3]) {
 #pragma unroll
-  for (int r = 0; r < ENC_ROWS; ++r)
-#pragma unroll
-    for (int d = 0; d < 3; ++d) put16<X3, BF16>(base, lo_delta, row + 32 * r, d, x[r][d]);
+  for (int d = 0; d < 3; ++d) put16<X3, BF16>(base, lo_delta, row, d, x[d]);
 #pragma unroll 1
   for (int f = 0; f < L; ++f) {
     const float sc = (float)(1 << f);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      float sn[ENC_ROWS], cs[ENC_ROWS];
-#pragma unroll
-      for (int r = 0; r < ENC_ROWS; ++r) {
-        const float v = x[r][d] * sc;  // exact (power of two)
-        sn[r] = sinf(v);
-        cs[r] = sinf(__fadd_rn(v, AON_HALF_PI_F));
-      }
-#pragma unroll
-      for (int r = 0; r < ENC_ROWS; ++r) {
-        put16<X3, BF16>(base, lo_delta, row + 32 * r, 3 + 3 * f + d, sn[r]);
-        put16<X3, BF16>(base, lo_delta, row + 32 * r, 3 + 3 * L + 3 * f + d, cs[r]);
-      }
+      const float v = x[d] * sc;  // exact (power of two)
+      const float sn = sinf(v);
+      const float cs = sinf(__fadd_rn(v, AON_HALF_PI_F));
+      put16<X3, BF16>(base, lo_delta, row, 3 + 3 * f + d, sn);
+      put16<X3, BF16>(base, lo_delta, row, 3 + 3 * L + 3 * f + d, cs);
     }
   }
 #pragma unroll
-  for (int k = 3 + 6 * L; k < NK; ++k)
-#pragma unroll
-    for (int r = 0; r < ENC_ROWS; ++r) put16<X3, BF16>(base, lo_delta, row + 32 * r, k, 0.f);
+  for (int k = 3 + 6 * L; k < NK; ++k) put16<X3, BF16>(base, lo_delta, row, k, 0.f);
 }
 
 template <bool X3, bool BF16>
@@ -492,6 +517,22 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo32) {
 // named barrier shared by the two epilogue warps of a TMEM lane quadrant (ids 1..4)
 __device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void pair_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+// named barrier of the epilogue + encoder warps (0-11) around the in-kernel hierarchical sampling of the fused kernel
+__device__ __forceinline__ void level_bar_sync() { asm volatile("bar.sync 5, 384;" ::: "memory"); }
+
+// ray `row` of this CTA's tile: origin, direction, view direction (clamped to the last ray for the padding rows)
+__device__ __forceinline__ void load_ray(const TcParams& p, int row, float (&o)[3], float (&d)[3], float (&v)[3]) {
+  const long ray = (long)blockIdx.x * 128 + row;
+  const long rl = ray < p.R ? ray : (long)p.R - 1;
+  if (p.cam_on) {
+    ray_from_camera(p.ray0 + rl, p.img_H, p.img_W, p.focal, p.cam, o, d);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = d[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = p.rays_o[3 * rl + k]; d[k] = p.rays_d[3 * rl + k]; v[k] = p.viewdirs[3 * rl + k]; }
+  }
+}
 
 template <int KIND, bool X3, bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_constant__ TcParams p) {
@@ -505,13 +546,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   const uint32_t bars = sm_u32 + SP::BARS;
   auto bar = [&](int slot) { return bars + 8u * slot; };
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(sm + SP::BARS + 8 * BAR_TMEM);
+  volatile uint32_t* s_words = reinterpret_cast<volatile uint32_t*>(sm + SP::BARS);
+  const uint32_t ticket = bars + 4u * WORD_TICKET;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = ptx::cluster_ctarank();   // 0 = leader (issues the pair's MMAs), 1 = peer
   const Program& P = p.prog;
-  // This CTA composites samples [s0, s0 + S) of its rays (S = local count); SG = samples per ray.
-  const int s0 = (int)blockIdx.y * p.seg_len, SG = p.S;
-  const int S = min(p.seg_len, SG - s0);
+  // Level 0: this CTA composites samples [s0, s0 + S_first) of its rays (a classic launch may cut the sample range into
+  // segments, blockIdx.y); the fused kernel (n_levels == 2) walks all of level 0, samples the fine positions in-kernel
+  // and walks all of level 1.
+  const int n_levels = p.n_levels;
+  const int s0 = (int)blockIdx.y * p.seg_len;
+  const int S_first = min(p.seg_len, p.S_level[0] - s0);
+  const int total_planes = S_first + (n_levels == 2 ? p.S_level[1] : 0);
   constexpr int NSTAGE = SP::NSTAGE;
   constexpr int E_OFF = off_E(X3), V_OFF = off_V(X3), P_OFF = off_P(X3), ONE_OFF = off_ONE(X3);
 
@@ -526,6 +573,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     ptx::mbar_init(bar(BAR_EFREE), 2);   // both MMA issuers commit it
     ptx::mbar_init(bar(BAR_XW), 4);
     ptx::fence_mbar_init();
+    s_words[WORD_TICKET] = 0u;
+    uint32_t slot = 0;
+    if (n_levels == 2) {
+      // one scratch slot per resident CTA; n_slots >= number of SMs and one CTA fits per SM, so a free one exists
+      for (uint32_t i = blockIdx.x % p.n_slots, tries = 0;; i = (i + 1 == (uint32_t)p.n_slots ? 0 : i + 1)) {
+        const unsigned bit = 1u << (i & 31);
+        if (!(atomicOr(p.slot_mask + (i >> 5), bit) & bit)) { slot = i; break; }
+        if (++tries > (1u << 22)) {
+          if (p.err_flag) atomicExch(p.err_flag, 9);
+          __threadfence_system();
+          __trap();
+        }
+      }
+    }
+    s_words[WORD_SLOT] = slot;
   }
   if (warp == 8) {
     ptx::tmem_alloc2(sm_u32 + SP::BARS + 8 * BAR_TMEM, 512);
@@ -533,12 +595,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   }
   {
     // head weights -> shared memory: [deform 3x128 + 4,] density 1x256 + 4, rgb 3x128 + 4 (PackedLayout::head_* order)
+    // (both levels share the layout; the fused kernel reloads them between the levels)
     int off = 0;
     constexpr int NHEAD = KIND == AON_KIND_VANILLA ? 2 : 3;
     for (int h = 0; h < NHEAD; ++h) {
       const int n = (KIND == AON_KIND_AUTODECODER ? (h == 1 ? 256 : 384) : (h == 0 ? 256 : 384));
-      const float* w = reinterpret_cast<const float*>(p.packed + p.L.head_w[h]);
-      const float* b = reinterpret_cast<const float*>(p.packed + p.L.head_b[h]);
+      const float* w = reinterpret_cast<const float*>(p.packed[0] + p.L.head_w[h]);
+      const float* b = reinterpret_cast<const float*>(p.packed[0] + p.L.head_b[h]);
       for (int i = tid; i < n; i += TC_THREADS) s_par[off + i] = w[i] * (1.0f / SCALE_A);
       if (tid < 4) s_par[off + n + tid] = b[tid];
       off += n + 4;
@@ -571,6 +634,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   auto mark = [&](int role, int s, int ui, int ev) {
     if (p.tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && s < 4) p.tl[((role * 4 + s) * MAX_UNITS + ui) * 4 + ev] = clock64() - t_start;
   };
+  // fused kernel: this CTA's scratch slot = coarse weights [128][S0] then fine t [128][S1]  (L2-resident: __ldcg / __stcg)
+  const int S0L = p.S_level[0], S1L = p.S_level[1];
+  float* slot_w = p.slots + (size_t)s_words[WORD_SLOT] * (size_t)(128 * (S0L + S1L));
+  float* slot_t1 = slot_w + 128 * S0L;
+  // In-kernel hierarchical sampling between the levels (A7; sampling.cuh), by the 12 epilogue + encoder warps: every
+  // compositing weight of level 0 is in the slot, all MMAs of level 0 have completed (the epilogue warps waited for the
+  // last accumulator), so the hidden-activation region of shared memory is free and serves as the per-warp scratch.
+  auto sample_fine_positions = [&]() {
+    level_bar_sync();
+    float* scr = reinterpret_cast<float*>(sm + OFF_A) + warp * 384;
+    static_assert(PDF_SCRATCH_FLOATS <= 384, "per-warp sampling scratch");
+    for (int r = warp; r < 128; r += 12) {
+      const long ray_r = (long)blockIdx.x * 128 + r;
+      const long rl_r = ray_r < p.R ? ray_r : (long)p.R - 1;
+      sample_pdf_ray<true>(p.t_vals + (p.t_stride ? rl_r * p.t_stride : 0), slot_w + r * S0L,
+                           p.u ? p.u + rl_r * p.u_stride : nullptr, S0L, S1L - S0L, scr, slot_t1 + r * S1L, lane);
+    }
+    level_bar_sync();
+  };
 
   if (warp >= 12) {
     ptx::setmaxnreg_dec<REGS_CONTROL>();
@@ -578,23 +660,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     // ================================ weight producer ================================
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
-      const char* fold_src = reinterpret_cast<const char*>(p.folded + FOLD_STAGE_FLOAT0) + (size_t)rank * P.fold_half_bytes;
-      for (int s = 0; s < S; ++s) {
-        const char* src = p.packed + (size_t)rank * P.stream_bytes;
-        for (int ui = 0; ui < P.n_units; ++ui) {
-          const Unit& u = P.u[ui];
-          for (int c = 0; c < u.n_chunks; ++c) {
-            const uint32_t w = u.ch[c];
-            const uint32_t bytes = (uint32_t)stage_bytes(u, w, X3);
-            const int nst = chunk_stages(w, X3);
-            for (int i = 0; i < nst; ++i) {
-              const char* from = src;
-              if (KIND == AON_KIND_AUTODECODER && c == 0 && u.fold >= 0) from = fold_src + (size_t)u.fold * 16;
-              spin_bar(bar(BAR_EMPTY + slot), phase ^ 1);
-              ptx::mbar_arrive_expect_tx(bar(BAR_FULL + slot), bytes);
-              ptx::bulk_g2s(sm_u32 + SP::RING + slot * SP::STAGE, from, bytes, bar(BAR_FULL + slot));
-              src += bytes;
-              if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+      for (int level = 0; level < n_levels; ++level) {
+        const int S = level == 0 ? S_first : S1L;
+        const char* fold_src = reinterpret_cast<const char*>(p.folded[level] + FOLD_STAGE_FLOAT0) + (size_t)rank * P.fold_half_bytes;
+        for (int s = 0; s < S; ++s) {
+          const char* src = p.packed[level] + (size_t)rank * P.stream_bytes;
+          for (int ui = 0; ui < P.n_units; ++ui) {
+            const Unit& u = P.u[ui];
+            for (int c = 0; c < u.n_chunks; ++c) {
+              const uint32_t w = u.ch[c];
+              const uint32_t bytes = (uint32_t)stage_bytes(u, w, X3);
+              const int nst = chunk_stages(w, X3);
+              for (int i = 0; i < nst; ++i) {
+                const char* from = src;
+                if (KIND == AON_KIND_AUTODECODER && c == 0 && u.fold >= 0) from = fold_src + (size_t)u.fold * 16;
+                spin_bar(bar(BAR_EMPTY + slot), phase ^ 1);
+                ptx::mbar_arrive_expect_tx(bar(BAR_FULL + slot), bytes);
+                ptx::bulk_g2s(sm_u32 + SP::RING + slot * SP::STAGE, from, bytes, bar(BAR_FULL + slot));
+                src += bytes;
+                if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+              }
             }
           }
         }
@@ -606,7 +691,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
       // mbarrier.try_wait is CTA-local, so the leader cannot watch this CTA's FULL barriers: forward each
       // "my half of the stage landed" to the leader's FULL barrier (count 2) in stage order.
       uint32_t slot = 0, phase = 0;
-      for (int s = 0; s < S; ++s) {
+      for (int s = 0; s < total_planes; ++s) {
         for (int ui = 0; ui < P.n_units; ++ui) {
           const Unit& u = P.u[ui];
           int nst = 0;
@@ -625,9 +710,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
       // Issuing one weight stage (barrier test + fence + 2-3 tcgen05.mma + commit) costs one thread ~400 cycles of
       // serial latency (measured) -- as long as the MMAs of the stage take to execute -- so a single issuer cannot
       // keep the tensor pipe fed.  Two threads in different warps take alternate stages (global stage number
-      // parity).  All MMAs of a unit accumulate into the same TMEM tile, which commutes; nothing overwrites (the
-      // epilogue zeroes the accumulator as it drains it).  tcgen05.commit tracks the committing thread's own MMAs, so
-      // both commit the accumulator-full (and encoding-free) barriers, which count 2.
+      // parity) and hand an issue ticket back and forth (ticket_wait above), so the MMAs enter the tensor core in stage
+      // order: all waiting and the commits of the two threads overlap, only the issue itself is serialised.
+      // tcgen05.commit tracks the committing thread's own MMAs, so both commit the accumulator-full (and
+      // encoding-free) barriers, which count 2.
       const uint32_t me = warp == 14 ? 0u : 1u;
       constexpr uint32_t IDESC128 = ptx::idesc_f16(256, 128, BF16 ? 1 : 0);   // M = 256 over the pair
       constexpr uint32_t IDESC256 = ptx::idesc_f16(256, 256, BF16 ? 1 : 0);
@@ -640,7 +726,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
         if (slot >= (uint32_t)NSTAGE) { slot -= NSTAGE; phase ^= 1; }
       };
       auto chunk_parity = [&](uint32_t w, int smp) { return (((uint32_t)smp & (w >> 21)) ^ (w >> 22)) & 1u; };
-      for (int s = 0; s < S; ++s) {
+      for (int s = 0; s < total_planes; ++s) {
         for (int ui = 0; ui < P.n_units; ++ui, ++g) {
           const Unit& u = P.u[ui];
           const uint32_t b = g & 1;
@@ -650,8 +736,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           const uint32_t b_kstep16 = n128 * 128u;               // one K=16 step of B: N/2 * 32 B, >> 4
           const int n_chunks = u.n_chunks;
           const uint32_t d_tmem = tmem_base + b * 256u;
-          // Every MMA of a unit accumulates (the epilogue leaves the accumulator zeroed), so the two issuers need no
-          // ordering between their MMAs; both wait for the accumulator to be drained before their first one.
+          // Every MMA of a unit accumulates (the epilogue leaves the accumulator zeroed); both issuers wait for the
+          // accumulator to be drained before their first one.
           bool unit_wait = true;
           if ((n & 1u) == me) {
             // chunk 0 = bias rows x ones columns (one MMA in every mode)
@@ -661,7 +747,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
             ptx::tc_fence_after();
             if (me == 0) mark(0, s, ui, 0);
             const uint32_t bd = (ring16 + slot * (SP::STAGE >> 4)) | b_lbo;
+            ticket_wait(ticket, n);
             ptx::mma2_f16_ss(d_tmem, mk_desc((base16 + (u.ch[0] & 0xFFFFu)) | A_LBO), mk_desc(bd), idesc, 1);
+            ticket_set(ticket, n + 1u);
             ptx::mma_commit2(bar(BAR_EMPTY + slot), 3);
           }
           advance(1);
@@ -690,6 +778,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
               ptx::tc_fence_after();
               const uint32_t bd = (ring16 + my_slot * (SP::STAGE >> 4)) | b_lbo;
               const uint32_t a_hi = ((base16 + (w & 0xFFFFu)) | A_LBO) + (X3 ? ks * 256u : 0u);
+              ticket_wait(ticket, n + ks);
               if (X3) {   // hi rows; lo rows follow at +N/2*32 B
                 const uint32_t a_lo = a_hi + (((w >> 26) & 31u) << 8);  // (lo offset >> 12) << 12 >> 4
                 ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi), mk_desc(bd), idesc, 1);
@@ -700,6 +789,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
                 for (uint32_t k = 0; k < nk; ++k)
                   ptx::mma2_f16_ss(d_tmem, mk_desc(a_hi + k * 256u), mk_desc(bd + k * b_kstep16), idesc, 1);
               }
+              ticket_set(ticket, n + ks + 1u);
               ptx::mma_commit2(bar(BAR_EMPTY + my_slot), 3);
             }
             advance(nst);
@@ -722,75 +812,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
   } else if (warp >= 8) {
     ptx::setmaxnreg_dec<REGS_ENCODER>();
     // ================================ encoder: sample positions -> operand chunks ================================
-    const int row = tid - 256;   // one row per encoder thread (ENC_ROWS == 1; rows row + 32 r otherwise)
-    float o[ENC_ROWS][3], d[ENC_ROWS][3];
-    const float* tv[ENC_ROWS];
-#pragma unroll
-    for (int r = 0; r < ENC_ROWS; ++r) {
-      const long ray = (long)blockIdx.x * 128 + row + 32 * r;
-      const long rl = ray < p.R ? ray : (long)p.R - 1;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { o[r][k] = p.rays_o[3 * rl + k]; d[r][k] = p.rays_d[3 * rl + k]; }
-      tv[r] = p.t_vals + (p.t_stride ? rl * p.t_stride : 0);
-    }
+    const int row = tid - 256;   // one row per encoder thread
+    float o[3], d[3], vd[3];
+    load_ray(p, row, o, d, vd);
+    const long ray = (long)blockIdx.x * 128 + row;
+    const long rl = ray < p.R ? ray : (long)p.R - 1;
     auto publish = [&](int id) {
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_CHUNK + id));
     };
-    {  // view-direction encoding, once per tile (model.py:174: pos_enc(viewdirs, 0, 4))
-      float v[ENC_ROWS][3];
+    // view-direction encoding, once per tile (model.py:174: pos_enc(viewdirs, 0, 4))
+    encode_store<4, 32, X3, BF16>(sm + V_OFF, LO_V, row, vd);
+    publish(CH_V);
+    int pl = 0;   // plane number over both levels (barrier parities continue across the level boundary)
+    for (int level = 0; level < n_levels; ++level) {
+      const int S = level == 0 ? S_first : S1L;
+      const int SG = level == 0 ? S0L : S1L;
+      const int sb = level == 0 ? s0 : 0;
+      if (level == 1) sample_fine_positions();
+      const float* tv = level == 0 ? p.t_vals + (p.t_stride ? rl * p.t_stride : 0) : slot_t1 + row * S1L;
+      float t = __ldcg(tv + sb);
+      for (int s = 0; s < S; ++s, ++pl) {
+        const float t_next = (sb + s + 1 < SG) ? __ldcg(tv + sb + s + 1) : 0.f;
+        // cast_rays (helper.py:25-26)
+        float x[3];
 #pragma unroll
-      for (int r = 0; r < ENC_ROWS; ++r) {
-        const long ray = (long)blockIdx.x * 128 + row + 32 * r;
-        const long rl = ray < p.R ? ray : (long)p.R - 1;
+        for (int k = 0; k < 3; ++k) x[k] = __fadd_rn(o[k], __fmul_rn(t, d[k]));
+        if (pl > 0) wait_bar(bar(BAR_EFREE), (uint32_t)((pl - 1) & 1), p.err_flag, 7);
+        if (tid == 256) mark(2, pl, 0, 0);
+        if (KIND == AON_KIND_AUTODECODER) {
+          // raw position -> operand chunk P (deformation MLP input; model_autodecoder.py:196-198)
+          constexpr int PK = X3 ? 16 : 32;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) v[r][k] = p.viewdirs[3 * rl + k];
-      }
-      encode_store<4, 32, X3, BF16>(sm + V_OFF, LO_V, row, v);
-      publish(CH_V);
-    }
-    float t[ENC_ROWS];
+          for (int k = 0; k < 3; ++k) put16<X3, BF16>(sm + P_OFF, LO_P, row, k, x[k]);
 #pragma unroll
-    for (int r = 0; r < ENC_ROWS; ++r) t[r] = tv[r][s0];
-    for (int s = 0; s < S; ++s) {
-      float t_next[ENC_ROWS];
+          for (int k = 3; k < PK; ++k) put16<X3, BF16>(sm + P_OFF, LO_P, row, k, 0.f);
+          publish(CH_P);
+          // warped position x' = x + deformation(x), handed over by the epilogue warps as fp32 in the
+          // (by then consumed) P region
+          wait_bar(bar(BAR_XW), (uint32_t)(pl & 1), p.err_flag, 8);
+          const float* xw = reinterpret_cast<const float*>(sm + P_OFF);
 #pragma unroll
-      for (int r = 0; r < ENC_ROWS; ++r) t_next[r] = (s0 + s + 1 < SG) ? tv[r][s0 + s + 1] : 0.f;
-      // cast_rays (helper.py:25-26)
-      float x[ENC_ROWS][3];
-#pragma unroll
-      for (int r = 0; r < ENC_ROWS; ++r)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) x[r][k] = __fadd_rn(o[r][k], __fmul_rn(t[r], d[r][k]));
-      if (s > 0) wait_bar(bar(BAR_EFREE), (uint32_t)((s - 1) & 1), p.err_flag, 7);
-      if (tid == 256) mark(2, s, 0, 0);
-      if (KIND == AON_KIND_AUTODECODER) {
-        // raw position -> operand chunk P (deformation MLP input; model_autodecoder.py:196-198)
-        constexpr int PK = X3 ? 16 : 32;
-#pragma unroll
-        for (int r = 0; r < ENC_ROWS; ++r) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) put16<X3, BF16>(sm + P_OFF, LO_P, row + 32 * r, k, x[r][k]);
-#pragma unroll
-          for (int k = 3; k < PK; ++k) put16<X3, BF16>(sm + P_OFF, LO_P, row + 32 * r, k, 0.f);
+          for (int k = 0; k < 3; ++k) x[k] = xw[128 * k + row];
         }
-        publish(CH_P);
-        // warped position x' = x + deformation(x), handed over by the epilogue warps as fp32 in the
-        // (by then consumed) P region
-        wait_bar(bar(BAR_XW), (uint32_t)(s & 1), p.err_flag, 8);
-        const float* xw = reinterpret_cast<const float*>(sm + P_OFF);
-#pragma unroll
-        for (int r = 0; r < ENC_ROWS; ++r)
-#pragma unroll
-          for (int k = 0; k < 3; ++k) x[r][k] = xw[128 * k + row + 32 * r];
+        encode_store<10, 64, X3, BF16>(sm + E_OFF, LO_E, row, x);
+        publish(CH_E0);
+        publish(CH_E0 + 1);
+        if (tid == 256) mark(2, pl, 0, 1);
+        t = t_next;
       }
-      encode_store<10, 64, X3, BF16>(sm + E_OFF, LO_E, row, x);
-      publish(CH_E0);
-      publish(CH_E0 + 1);
-      if (tid == 256) mark(2, s, 0, 1);
-#pragma unroll
-      for (int r = 0; r < ENC_ROWS; ++r) t[r] = t_next[r];
     }
   } else {
     ptx::setmaxnreg_inc<REGS_EPILOGUE>();
@@ -802,10 +873,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     const long ray = (long)blockIdx.x * 128 + row;
     const bool valid = ray < p.R;
     const long rl = valid ? ray : (long)p.R - 1;
-    const float ox = p.rays_o[3 * rl + 0], oy = p.rays_o[3 * rl + 1], oz = p.rays_o[3 * rl + 2];
-    const float dx = p.rays_d[3 * rl + 0], dy = p.rays_d[3 * rl + 1], dz = p.rays_d[3 * rl + 2];
+    float ro[3], rd[3], rv[3];
+    load_ray(p, row, ro, rd, rv);
+    const float ox = ro[0], oy = ro[1], oz = ro[2], dx = rd[0], dy = rd[1], dz = rd[2];
     const float dnorm = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-    const float* tv = p.t_vals + (p.t_stride ? rl * p.t_stride : 0);
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
 
     // head weights / biases in shared memory
@@ -813,11 +884,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     const float* hw_sig = s_par + (KIND == AON_KIND_AUTODECODER ? 388 : 0);
     const float* hw_rgb = hw_sig + 260;
 
-    float trans = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cdepth = 0.f, cacc = 0.f;
-    float t_cur = tv[s0];
     uint32_t g = 0;
-    for (int s = 0; s < S; ++s) {
-      const float t_next = (s0 + s + 1 < SG) ? tv[s0 + s + 1] : 0.f;
+    int pl = 0;
+    for (int level = 0; level < n_levels; ++level) {
+      const int S = level == 0 ? S_first : S1L;
+      const int SG = level == 0 ? S0L : S1L;
+      const int sb = level == 0 ? s0 : 0;
+      if (level == 1) {
+        sample_fine_positions();
+        // the fine MLP's head weights replace the coarse ones (all 12 warps are past the level barrier: nobody reads them)
+        int off = 0;
+        constexpr int NHEAD = KIND == AON_KIND_VANILLA ? 2 : 3;
+        for (int h = 0; h < NHEAD; ++h) {
+          const int n = (KIND == AON_KIND_AUTODECODER ? (h == 1 ? 256 : 384) : (h == 0 ? 256 : 384));
+          const float* w = reinterpret_cast<const float*>(p.packed[1] + p.L.head_w[h]);
+          const float* b = reinterpret_cast<const float*>(p.packed[1] + p.L.head_b[h]);
+          for (int i = tid; i < n; i += 256) s_par[off + i] = w[i] * (1.0f / SCALE_A);
+          if (tid < 4) s_par[off + n + tid] = b[tid];
+          off += n + 4;
+        }
+        asm volatile("bar.sync 6, 256;" ::: "memory");
+      }
+      const float* tv = level == 0 ? p.t_vals + (p.t_stride ? rl * p.t_stride : 0) : slot_t1 + row * S1L;
+      const bool last_level = level == n_levels - 1;
+      float trans = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cdepth = 0.f, cacc = 0.f;
+      float t_cur = __ldcg(tv + sb);
+    for (int s = 0; s < S; ++s, ++pl) {
+      const float t_next = (sb + s + 1 < SG) ? __ldcg(tv + sb + s + 1) : 0.f;
       float sig = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f;  // head accumulators (density; rgb / deformation)
 
       for (int ui = 0; ui < P.n_units; ++ui, ++g) {
@@ -831,7 +924,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
         unsigned char* out_base = sm + OFF_A + row * 16;
         wait_bar(bar(BAR_DFULL + b), (g >> 1) & 1, p.err_flag, 5);
         ptx::tc_fence_after();
-        if (tid == 0) mark(1, s, ui, 0);
+        if (tid == 0) mark(1, pl, ui, 0);
         const uint32_t d_addr = lane_base + b * 256u + (uint32_t)half * 32u;
 
         uint32_t r[2][32];
@@ -861,7 +954,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_DEMPTY + b));
           }
-          if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && s == 0) {
+          if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && pl == 0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) p.dbg[((size_t)ui * 128 + row) * 256 + cc * 32 + i] = v[i] * (1.0f / SCALE_A);
           }
@@ -899,10 +992,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_CHUNK + cc));
-            if (tid == 0 && j == 0) mark(1, s, ui, 1);
+            if (tid == 0 && j == 0) mark(1, pl, ui, 1);
           }
         }
-        if (tid == 0) mark(1, s, ui, 2);
+        if (tid == 0) mark(1, pl, ui, 2);
 
         // head partial sums of the odd warp -> even warp (owner of the per-ray state)
         if (epi != EPI_STORE) {
@@ -945,33 +1038,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           bb = __fsub_rn(__fmul_rn(sigmoidf_ref(bb), 1.002f), 0.001f);
           sigma = softplusf_ref(__fadd_rn(raw_sigma, -1.0f));
         }
-        const float delta = (s0 + s + 1 < SG) ? __fsub_rn(t_next, t_cur) : 1e10f;
+        const float delta = (sb + s + 1 < SG) ? __fsub_rn(t_next, t_cur) : 1e10f;
         const float dist = __fmul_rn(delta, dnorm);
         const float alpha = __fsub_rn(1.0f, expf(__fmul_rn(-sigma, dist)));
-        const float w = __fmul_rn(alpha, trans);
-        cr = fmaf(w, rr, cr); cg = fmaf(w, gg, cg); cb = fmaf(w, bb, cb);
-        cdepth = fmaf(w, t_cur, cdepth);
-        cacc += w;
-        trans = __fmul_rn(trans, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
-        if (p.weights && valid) p.weights[ray * SG + s0 + s] = w;   // segment-local weight when n_seg > 1 (scaled later)
+        if (p.n_seg > 1) {
+          // sample-segmented launch: the ray's samples are composited in order by composite_samples_kernel
+          if (valid) p.seg_samples[ray * SG + sb + s] = make_float4(alpha, rr, gg, bb);
+        } else {
+          const float w = __fmul_rn(alpha, trans);
+          cr = fmaf(w, rr, cr); cg = fmaf(w, gg, cg); cb = fmaf(w, bb, cb);
+          cdepth = fmaf(w, t_cur, cdepth);
+          cacc += w;
+          trans = __fmul_rn(trans, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
+          if (n_levels == 2) {
+            if (level == 0) __stcg(slot_w + row * S0L + s, w);
+          } else if (p.weights && valid) {
+            p.weights[ray * SG + s] = w;
+          }
+        }
       }
       t_cur = t_next;
     }
 
-    if (valid && owner && p.n_seg > 1) {
-      float4* pp = reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.y * p.R + ray) * 8);
-      pp[0] = make_float4(trans, cr, cg, cb);
-      pp[1] = make_float4(cdepth, cacc, 0.f, 0.f);
-    } else if (valid && owner) {
-      if (isnan(cdepth)) cdepth = INFINITY;  // helper.py:179 nan_to_num(depth, nan=inf)
-      else if (isinf(cdepth)) cdepth = cdepth > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
-      if (p.white_bkgd) {
-        const float bg = __fsub_rn(1.0f, cacc);
-        cr += bg; cg += bg; cb += bg;
+      if (valid && owner && p.n_seg == 1) {
+        if (isnan(cdepth)) cdepth = INFINITY;  // helper.py:179 nan_to_num(depth, nan=inf)
+        else if (isinf(cdepth)) cdepth = cdepth > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+        if (p.white_bkgd) {
+          const float bg = __fsub_rn(1.0f, cacc);
+          cr += bg; cg += bg; cb += bg;
+        }
+        float* o5 = last_level ? p.out5 : p.coarse_out5;
+        if (o5 != nullptr) {
+          o5[5 * ray + 0] = cr; o5[5 * ray + 1] = cg; o5[5 * ray + 2] = cb; o5[5 * ray + 3] = cacc; o5[5 * ray + 4] = cdepth;
+        } else if (last_level) {
+          p.comp_rgb[3 * ray + 0] = cr; p.comp_rgb[3 * ray + 1] = cg; p.comp_rgb[3 * ray + 2] = cb;
+          p.acc[ray] = cacc;
+          p.depth[ray] = cdepth;
+        }
       }
-      p.comp_rgb[3 * ray + 0] = cr; p.comp_rgb[3 * ray + 1] = cg; p.comp_rgb[3 * ray + 2] = cb;
-      p.acc[ray] = cacc;
-      p.depth[ray] = cdepth;
     }
   }
 
@@ -982,37 +1086,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     ptx::tc_fence_after();
     ptx::tmem_dealloc2(tmem_base, 512);
   }
+  if (tid == 0 && n_levels == 2) {
+    const uint32_t slot = s_words[WORD_SLOT];
+    atomicAnd(p.slot_mask + (slot >> 5), ~(1u << (slot & 31)));
+  }
 }
 
-// Folds the per-segment partial composites of one ray in sample order:  C += T * C_seg,  T *= T_seg  (the exclusive
-// transmittance product of helper.py:170-176 re-associated at the segment boundaries), scales the segment-local
-// weights by the transmittance in front of their segment, then applies the final nan/white-background handling.
-__global__ void combine_segments_kernel(const float* __restrict__ partial, int R, int S, int n_seg, int seg_len, int white_bkgd,
-                                        float* __restrict__ comp_rgb, float* __restrict__ acc, float* __restrict__ depth,
-                                        float* __restrict__ weights) {
-  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+// Sample-segmented launches (small ray batches, the tail wave of a large one) leave (alpha, r, g, b) of every sample in a
+// scratch tensor; this kernel composites them per ray in sample order with exactly the operation sequence of the fused
+// kernel's epilogue (helper.py:157-195), so a segmented render is bit-identical to an unsegmented one.
+__global__ void composite_samples_kernel(const float4* __restrict__ smp, const float* __restrict__ t_vals, long t_stride, int R, int S,
+                                         int white_bkgd, float* __restrict__ comp_rgb, float* __restrict__ acc,
+                                         float* __restrict__ depth, float* __restrict__ out5, float* __restrict__ weights) {
+  const long ray = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (ray >= R) return;
-  float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, ca = 0.f;
-  for (int g = 0; g < n_seg; ++g) {
-    const float4 a = *reinterpret_cast<const float4*>(partial + ((size_t)g * R + ray) * 8);
-    const float4 b = *reinterpret_cast<const float4*>(partial + ((size_t)g * R + ray) * 8 + 4);
-    cr = fmaf(T, a.y, cr); cg = fmaf(T, a.z, cg); cb = fmaf(T, a.w, cb);
-    cd = fmaf(T, b.x, cd); ca = fmaf(T, b.y, ca);
-    if (weights != nullptr && g > 0) {
-      const int e = min(S, (g + 1) * seg_len);
-      for (int s = g * seg_len; s < e; ++s) weights[(size_t)ray * S + s] *= T;
-    }
-    T *= a.x;
+  const float* tv = t_vals + (t_stride ? ray * t_stride : 0);
+  float trans = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cdepth = 0.f, cacc = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float4 a = smp[ray * S + s];
+    const float t_cur = tv[s];
+    const float w = __fmul_rn(a.x, trans);
+    cr = fmaf(w, a.y, cr); cg = fmaf(w, a.z, cg); cb = fmaf(w, a.w, cb);
+    cdepth = fmaf(w, t_cur, cdepth);
+    cacc += w;
+    trans = __fmul_rn(trans, __fadd_rn(__fsub_rn(1.0f, a.x), 1e-10f));
+    if (weights != nullptr) weights[ray * S + s] = w;
   }
-  if (isnan(cd)) cd = INFINITY;
-  else if (isinf(cd)) cd = cd > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+  if (isnan(cdepth)) cdepth = INFINITY;
+  else if (isinf(cdepth)) cdepth = cdepth > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
   if (white_bkgd) {
-    const float bg = __fsub_rn(1.0f, ca);
+    const float bg = __fsub_rn(1.0f, cacc);
     cr += bg; cg += bg; cb += bg;
   }
-  comp_rgb[3 * (size_t)ray + 0] = cr; comp_rgb[3 * (size_t)ray + 1] = cg; comp_rgb[3 * (size_t)ray + 2] = cb;
-  acc[ray] = ca;
-  depth[ray] = cd;
+  if (out5 != nullptr) {
+    out5[5 * ray + 0] = cr; out5[5 * ray + 1] = cg; out5[5 * ray + 2] = cb; out5[5 * ray + 3] = cacc; out5[5 * ray + 4] = cdepth;
+  } else {
+    comp_rgb[3 * ray + 0] = cr; comp_rgb[3 * ray + 1] = cg; comp_rgb[3 * ray + 2] = cb;
+    acc[ray] = cacc;
+    depth[ray] = cdepth;
+  }
 }
 
 // Samples-per-CTA split: small ray batches (the reference's 3840-ray chunks = 15 CTA pairs on 74 pair slots) leave most
@@ -1030,12 +1142,6 @@ static int choose_segments(int pairs, int S, int pair_slots) {
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
-static float* g_dbg = nullptr;
-static int g_force_segments = 0;   // debug hook: > 0 forces the number of sample segments per ray
-static int g_no_tail_split = 0;    // debug hook: 1 = never split the last wave of a large batch
-static int* g_err = nullptr;
-static long long* g_tl = nullptr;
-
 template <int KIND, bool X3, bool BF16>
 static int launch(const TcParams& p, int grid, int grid_y, cudaStream_t st) {
   using SP = SmemPlan<KIND, X3>;
@@ -1059,96 +1165,158 @@ static int launch(const TcParams& p, int grid, int grid_y, cudaStream_t st) {
   return AON_OK;
 }
 
-// Renders rays [0, R) of the arrays in `p` (already offset by the caller) with n_seg sample segments per ray.
-static int render_range(TcParams p, int kind, int precision, int R, int n_seg, int dev, cudaStream_t st) {
-  const int S = p.S;
-  p.R = R;
-  const int grid = ((R + 255) / 256) * 2;   // CTA pairs; an odd last tile leaves the peer with no valid rays
-  p.n_seg = n_seg;
-  p.seg_len = (S + n_seg - 1) / n_seg;
-  p.partial = nullptr;
-  if (n_seg > 1) {
-    // stream-ordered temporary for the per-segment partial composites (released right after the combine kernel).
-    // The default pool hands freed memory back to the driver at every synchronisation (a real cudaMalloc, ~1 ms, on the
-    // next call): keep it cached.
-    static bool pool_tuned[64] = {false};
-    if (dev < 64 && !pool_tuned[dev]) {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
-      pool_tuned[dev] = true;
-    }
-    AON_CUDA_CHECK(cudaMallocAsync((void**)&p.partial, (size_t)n_seg * R * 8 * sizeof(float), st));
-  }
+static int launch_any(const TcParams& p, int kind, int precision, int grid, int grid_y, cudaStream_t st) {
   const bool van = kind == AON_KIND_VANILLA;
-  int rc = AON_E_ARG;
   switch (precision) {
     case AON_PREC_TC_F16X3:
-      rc = van ? launch<AON_KIND_VANILLA, true, false>(p, grid, n_seg, st) : launch<AON_KIND_AUTODECODER, true, false>(p, grid, n_seg, st);
-      break;
+      return van ? launch<AON_KIND_VANILLA, true, false>(p, grid, grid_y, st) : launch<AON_KIND_AUTODECODER, true, false>(p, grid, grid_y, st);
     case AON_PREC_TC_F16:
-      rc = van ? launch<AON_KIND_VANILLA, false, false>(p, grid, n_seg, st) : launch<AON_KIND_AUTODECODER, false, false>(p, grid, n_seg, st);
-      break;
+      return van ? launch<AON_KIND_VANILLA, false, false>(p, grid, grid_y, st) : launch<AON_KIND_AUTODECODER, false, false>(p, grid, grid_y, st);
     case AON_PREC_TC_BF16:
-      rc = van ? launch<AON_KIND_VANILLA, false, true>(p, grid, n_seg, st) : launch<AON_KIND_AUTODECODER, false, true>(p, grid, n_seg, st);
-      break;
+      return van ? launch<AON_KIND_VANILLA, false, true>(p, grid, grid_y, st) : launch<AON_KIND_AUTODECODER, false, true>(p, grid, grid_y, st);
     default:
       set_error("bad precision %d", precision);
+      return AON_E_ARG;
   }
-  if (n_seg > 1) {
-    if (rc == AON_OK) {
-      combine_segments_kernel<<<(R + 255) / 256, 256, 0, st>>>(p.partial, R, S, n_seg, p.seg_len, p.white_bkgd, p.comp_rgb, p.acc, p.depth, p.weights);
-      g_launches++;
-      if (cudaGetLastError() != cudaSuccess) { set_error("combine_segments_kernel launch failed"); rc = AON_E_CUDA; }
-    }
-    cudaFreeAsync(p.partial, st);
-  }
-  return rc;
 }
 
-int render_level_tc(int kind, int precision, const void* packed, const float* folded, const float* rays_o,
-                    const float* rays_d, const float* viewdirs, const float* t_vals, long t_stride, int R, int S,
-                    int white_bkgd, float* comp_rgb, float* acc, float* depth, float* weights, cudaStream_t st) {
-  int dev = 0, major = 0;
-  AON_CUDA_CHECK(cudaGetDevice(&dev));
-  AON_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+static int device_info(int* dev, int* sms) {
+  int major = 0;
+  AON_CUDA_CHECK(cudaGetDevice(dev));
+  AON_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, *dev));
   if (major != 10) {
     set_error("tensor-core precision modes need an sm_100 device (found compute capability %d.x)", major);
     return AON_E_UNSUPPORTED;
   }
-  TcParams p;
+  *sms = 148;
+  cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, *dev);
+  return AON_OK;
+}
+
+// Classic single-level launch over rays [0, R) of the arrays in `p` (already offset by the caller) with n_seg sample
+// segments per ray; seg_buf (>= R * S float4) is only touched when n_seg > 1.
+static int render_range(TcParams p, int kind, int precision, int R, int n_seg, float4* seg_buf, cudaStream_t st) {
+  const int S = p.S_level[0];
+  p.R = R;
+  const int grid = ((R + 255) / 256) * 2;   // CTA pairs; an odd last tile leaves the peer with no valid rays
+  p.n_seg = n_seg;
+  p.seg_len = (S + n_seg - 1) / n_seg;
+  p.seg_samples = n_seg > 1 ? seg_buf : nullptr;
+  int rc = launch_any(p, kind, precision, grid, n_seg, st);
+  if (n_seg > 1 && rc == AON_OK) {
+    composite_samples_kernel<<<(R + 127) / 128, 128, 0, st>>>(seg_buf, p.t_vals, p.t_stride, R, S, p.white_bkgd, p.comp_rgb, p.acc,
+                                                              p.depth, p.out5, p.weights);
+    g_launches++;
+    if (cudaGetLastError() != cudaSuccess) { set_error("composite_samples_kernel launch failed"); rc = AON_E_CUDA; }
+  }
+  return rc;
+}
+
+static void fill_common(TcParams& p, int kind, int precision, const AonRenderOpts* opts) {
+  memset(&p, 0, sizeof(p));
   p.prog = build_program(kind, precision);
   p.L = layout_tc(kind, precision);
-  p.packed = (const char*)packed;
-  p.folded = folded;
+  p.n_seg = 1;
+  if (opts) { p.dbg = opts->dbg; p.err_flag = opts->err_flag; p.tl = opts->timeline; }
+}
+
+size_t seg_bytes_tc(int R, int S) {
+  // worst case of the sample-segmented part of a launch: every ray of a small batch, or the last partial wave (< 80 CTA pairs)
+  const long rays = R < MAX_SLOTS / 2 * 256 ? R : MAX_SLOTS / 2 * 256;
+  return (size_t)rays * S * sizeof(float4);
+}
+
+// Split of a fused render of R rays: returns the number of rays (a multiple of 256, or R) the fused kernel takes as full
+// waves of CTA pairs; the remainder goes through the sample-segmented three-launch path.  A remainder that would not be
+// segmented anyway (it nearly fills a wave) stays in the fused launch.
+int tail_split_tc(int R, int sms, int* n_seg_coarse, int* n_seg_fine) {
+  const int pairs = (R + 255) / 256, slots = sms / 2;
+  const int rem = pairs % slots;
+  *n_seg_coarse = *n_seg_fine = 1;
+  if (rem == 0) return R;
+  const int nc = choose_segments(rem, N_COARSE, slots), nf = choose_segments(rem, N_TOTAL, slots);
+  if (nc == 1 && nf == 1) return R;
+  *n_seg_coarse = nc;
+  *n_seg_fine = nf;
+  return (pairs - rem) * 256;
+}
+
+int render_level_tc(int kind, int precision, const void* packed, const float* folded, const float* rays_o,
+                    const float* rays_d, const float* viewdirs, const float* t_vals, long t_stride, int R, int S,
+                    int white_bkgd, float* comp_rgb, float* acc, float* depth, float* out5, float* weights, void* workspace,
+                    size_t workspace_bytes, const AonRenderOpts* opts, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  int rc = device_info(&dev, &sms);
+  if (rc != AON_OK) return rc;
+  TcParams p;
+  fill_common(p, kind, precision, opts);
+  p.packed[0] = (const char*)packed;
+  p.folded[0] = folded;
+  p.S_level[0] = S;
+  p.n_levels = 1;
   p.rays_o = rays_o; p.rays_d = rays_d; p.viewdirs = viewdirs;
   p.t_vals = t_vals; p.t_stride = t_stride;
-  p.R = R; p.S = S; p.white_bkgd = white_bkgd;
-  p.comp_rgb = comp_rgb; p.acc = acc; p.depth = depth; p.weights = weights;
-  p.dbg = g_dbg;
-  p.err_flag = g_err;
-  p.tl = g_tl;
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  p.R = R; p.white_bkgd = white_bkgd;
+  p.comp_rgb = comp_rgb; p.acc = acc; p.depth = depth; p.out5 = out5; p.weights = weights;
+  float4* seg_buf = (float4*)workspace;
+  const size_t seg_cap = workspace_bytes / sizeof(float4);
   const int pairs = (R + 255) / 256, slots = sms / 2;
-  if (g_force_segments > 0) return render_range(p, kind, precision, R, g_force_segments <= S ? g_force_segments : 1, dev, st);
-  if (pairs <= slots || g_no_tail_split) return render_range(p, kind, precision, R, choose_segments(pairs, S, slots), dev, st);
+  const int force = opts ? opts->force_segments : 0;
+  auto need = [&](int rays, int n_seg) -> bool { return n_seg <= 1 || (size_t)rays * S <= seg_cap; };
+  if (force > 0) {
+    const int n = force <= S ? force : 1;
+    if (!need(R, n)) { set_error("aon_render_level: workspace too small for %d sample segments (see aon_workspace_bytes)", n); return AON_E_SIZE; }
+    return render_range(p, kind, precision, R, n, seg_buf, st);
+  }
+  if (pairs <= slots || (opts && opts->no_tail_split)) {
+    int n = choose_segments(pairs, S, slots);
+    if (!need(R, n)) n = 1;   // no workspace: unsegmented (slower on small batches, same values)
+    return render_range(p, kind, precision, R, n, seg_buf, st);
+  }
   // Large batch = several waves of ray tiles over the pair slots.  The last, partly filled wave (640x480: 1200 tiles on 74
   // slots = 16.2 waves) would hold all but a few SMs idle for a whole tile time: render the full waves unsplit and the
   // remainder tiles in a second launch with sample segments, so the remainder spreads over every SM.
   const int rem = pairs % slots;
-  const int n_tail = rem ? choose_segments(rem, S, slots) : 1;
-  if (n_tail == 1) return render_range(p, kind, precision, R, 1, dev, st);
+  int n_tail = rem ? choose_segments(rem, S, slots) : 1;
   const int R_main = (pairs - rem) * 256;
-  int rc = render_range(p, kind, precision, R_main, 1, dev, st);
+  if (n_tail > 1 && !need(R - R_main, n_tail)) n_tail = 1;
+  if (n_tail == 1) return render_range(p, kind, precision, R, 1, seg_buf, st);
+  rc = render_range(p, kind, precision, R_main, 1, seg_buf, st);
   if (rc != AON_OK) return rc;
   p.rays_o += 3 * (size_t)R_main; p.rays_d += 3 * (size_t)R_main; p.viewdirs += 3 * (size_t)R_main;
   p.t_vals += (size_t)R_main * t_stride;
-  p.comp_rgb += 3 * (size_t)R_main; p.acc += R_main; p.depth += R_main;
+  if (p.out5) p.out5 += 5 * (size_t)R_main;
+  else { p.comp_rgb += 3 * (size_t)R_main; p.acc += R_main; p.depth += R_main; }
   if (p.weights) p.weights += (size_t)R_main * S;
-  return render_range(p, kind, precision, R - R_main, n_tail, dev, st);
+  return render_range(p, kind, precision, R - R_main, n_tail, seg_buf, st);
+}
+
+// The fused image kernel over rays [0, R): coarse level, in-kernel hierarchical sampling, fine level in ONE launch; no
+// per-sample tensor reaches HBM.  slots / slot_mask live in the caller's workspace (mask zeroed by the caller).
+int render_fused_tc(int kind, int precision, const void* packed_c, const void* packed_f, const float* folded_c,
+                    const float* folded_f, const float* rays_o, const float* rays_d, const float* viewdirs, const Cam* cam,
+                    int H, int W, float focal, long ray0, const float* t0, long t0_stride, const float* u, long u_stride,
+                    int R, int S0, int S1, int white_bkgd, float* out5, float* coarse_out5, float* slots, unsigned* slot_mask,
+                    int n_slots, const AonRenderOpts* opts, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  int rc = device_info(&dev, &sms);
+  if (rc != AON_OK) return rc;
+  if (sms > n_slots) { set_error("fused render: device has %d SMs, workspace has %d scratch slots", sms, n_slots); return AON_E_UNSUPPORTED; }
+  TcParams p;
+  fill_common(p, kind, precision, opts);
+  p.packed[0] = (const char*)packed_c; p.packed[1] = (const char*)packed_f;
+  p.folded[0] = folded_c; p.folded[1] = folded_f;
+  p.S_level[0] = S0; p.S_level[1] = S1;
+  p.n_levels = 2;
+  p.rays_o = rays_o; p.rays_d = rays_d; p.viewdirs = viewdirs;
+  if (cam) { p.cam_on = 1; p.cam = *cam; p.img_H = H; p.img_W = W; p.focal = focal; p.ray0 = ray0; }
+  p.t_vals = t0; p.t_stride = t0_stride;
+  p.u = u; p.u_stride = u_stride;
+  p.slots = slots; p.slot_mask = slot_mask; p.n_slots = n_slots;
+  p.R = R; p.white_bkgd = white_bkgd;
+  p.seg_len = S0;
+  p.out5 = out5; p.coarse_out5 = coarse_out5;
+  return launch_any(p, kind, precision, ((R + 255) / 256) * 2, 1, st);
 }
 
 int pack_tail(int kind, const PackedLayout& L, const float* const* w, const float* const* b, char* packed,
@@ -1184,16 +1352,7 @@ extern "C" int aon_pack_weights_tc(int kind, int precision, const float* const* 
   return pack_tail(kind, L, w, b, (char*)packed, st);
 }
 
-// Debug hooks (not part of the public ABI in include/aon.h): a device buffer that receives the
-// pre-activation outputs of every unit for tile 0 / sample 0, and a device int that receives a code
-// if a barrier wait ever times out.
-extern "C" void aon_debug_set_buffers(float* dbg_dev, int* err_dev) {
-  g_dbg = dbg_dev;
-  g_err = err_dev;
-}
-extern "C" void aon_debug_set_timeline(long long* tl_dev) { g_tl = tl_dev; }
-extern "C" void aon_debug_force_segments(int n) { g_force_segments = n; }
-extern "C" void aon_debug_no_tail_split(int on) { g_no_tail_split = on; }
+// Introspection for tools / tests (not part of the public ABI in include/aon.h): program size and shared-memory plan.
 extern "C" int aon_debug_program_info(int kind, int precision, int* n_units, int* n_stages, int* smem_bytes) {
   const Program P = build_program(kind, precision);
   if (n_units) *n_units = P.n_units;

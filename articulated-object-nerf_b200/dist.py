@@ -18,7 +18,7 @@ import torch
 import torch.distributed as dist
 
 Tensor = torch.Tensor
-TILE = 128   # rays per CTA of the fused kernel; shard boundaries are tile aligned so no rank renders a ragged tile twice
+TILE = 256   # rays per CTA PAIR of the fused kernel; shard boundaries are pair aligned so only the image's last block is ragged
 
 
 def world() -> Tuple[int, int]:
@@ -40,6 +40,32 @@ def shard_bounds(n_rays: int, world_size: int, tile: int = TILE) -> list:
     return out
 
 
+def _gather_blocks(local: Tensor, bounds: list, rank: int, ws: int, gather: str) -> Optional[Tensor]:
+    """ONE collective per image.  Blocks of equal size (the usual case: the tile count divides by the world size) are
+    gathered straight into the result; ragged blocks are padded to the widest and trimmed after the gather."""
+    if ws == 1:
+        return local
+    widths = [h - l for l, h in bounds]
+    width = max(widths)
+    if min(widths) == width:
+        padded = local
+    else:
+        padded = local.new_zeros(width, local.shape[1])
+        padded[: widths[rank]] = local
+    if gather == "all":
+        out = local.new_empty(ws * width, local.shape[1])
+        dist.all_gather_into_tensor(out, padded)
+    else:
+        out = local.new_empty(ws * width, local.shape[1]) if rank == 0 else None
+        dist.gather(padded, list(out.view(ws, width, -1).unbind(0)) if rank == 0 else None, dst=0)
+        if rank != 0:
+            return None
+    if min(widths) == width:
+        return out
+    out = out.view(ws, width, -1)
+    return torch.cat([out[r, :w] for r, w in enumerate(widths)], 0)
+
+
 def render_sharded(render_fn: Callable[[Dict[str, Tensor]], Tensor], rays: Dict[str, Tensor],
                    gather: str = "all") -> Optional[Tensor]:
     """``rays``: the full per-image ray batch (identical on every rank: ``rays_o, rays_d, viewdirs`` [R,3]).
@@ -51,22 +77,19 @@ def render_sharded(render_fn: Callable[[Dict[str, Tensor]], Tensor], rays: Dict[
     lo, hi = bounds[rank]
     block = {k: v[lo:hi].contiguous() for k, v in rays.items() if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == R}
     local = render_fn(block) if hi > lo else rays["rays_o"].new_zeros(0, 5)
-    if ws == 1:
-        return local
-    # equal-size padded blocks -> a single all_gather_into_tensor (one NCCL collective per image)
-    width = max(h - l for l, h in bounds)
-    padded = local.new_zeros(width, local.shape[1])
-    padded[: hi - lo] = local
-    if gather == "all":
-        out = local.new_empty(ws * width, local.shape[1])
-        dist.all_gather_into_tensor(out, padded)
-    else:
-        out = local.new_empty(ws * width, local.shape[1]) if rank == 0 else None
-        dist.gather(padded, list(out.view(ws, width, -1).unbind(0)) if rank == 0 else None, dst=0)
-        if rank != 0:
-            return None
-    out = out.view(ws, width, -1)
-    return torch.cat([out[r, : h - l] for r, (l, h) in enumerate(bounds)], 0)
+    return _gather_blocks(local, bounds, rank, ws, gather)
+
+
+def render_image_sharded(render_block: Callable[[int, int], Tensor], n_rays: int, device=None,
+                         gather: str = "all") -> Optional[Tensor]:
+    """Camera form of ``render_sharded`` for the fused image kernel (``lib.render_image``: ray generation happens inside
+    the kernel, so no ray tensor exists to slice).  ``render_block(lo, hi) -> [hi - lo, 5]`` renders pixels [lo, hi) of
+    the image; every rank renders its contiguous, tile-aligned block and ONE all-gather assembles the [n_rays,5] image."""
+    rank, ws = world()
+    bounds = shard_bounds(n_rays, ws)
+    lo, hi = bounds[rank]
+    local = render_block(lo, hi) if hi > lo else torch.zeros(0, 5, dtype=torch.float32, device=device)
+    return _gather_blocks(local, bounds, rank, ws, gather)
 
 
 def allreduce_mean_(flat: Tensor) -> Tensor:

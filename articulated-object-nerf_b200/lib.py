@@ -33,9 +33,12 @@ SYMBOLS = {
     "aon_fold_latents": (_i, [_i, _i, _vp, _fp, _fp, _fp, _fp, _vp]),
     "aon_raygen": (_i, [_i, _i, _f, C.POINTER(_f), _fp, _fp, _vp]),
     "aon_sample_along_rays": (_i, [_f, _f, _i, _fp, _i, _fp, _vp]),
-    "aon_render_level": (_i, [_i, _i, _vp, _fp, _fp, _fp, _fp, _fp, _l, _i, _i, _i, _fp, _fp, _fp, _fp, _vp]),
+    "aon_workspace_bytes": (_sz, [_i, _i]),
+    "aon_render_level": (_i, [_i, _i, _vp, _fp, _fp, _fp, _fp, _fp, _l, _i, _i, _i, _fp, _fp, _fp, _fp, _vp, _sz, _vp, _vp]),
     "aon_sample_pdf": (_i, [_fp, _l, _fp, _fp, _l, _i, _i, _i, _fp, _vp]),
-    "aon_render_image_host": (_i, [_i, _i, _vp, _vp, _fp, _fp, _fp, _fp, _fp, _i, _f, _f, _i, _fp, _fp, _vp]),
+    "aon_render_rays": (_i, [_i, _i, _vp, _vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _f, _f, _i, _fp, _fp, _vp, _sz, _vp, _vp]),
+    "aon_render_image": (_i, [_i, _i, _vp, _vp, _fp, _fp, C.POINTER(_f), _f, _i, _i, _l, _i, _f, _f, _i, _fp, _fp, _vp, _sz, _vp, _vp]),
+    "aon_render_image_host": (_i, [_i, _i, _vp, _vp, _fp, _fp, _fp, _fp, _fp, _i, _f, _f, _i, _fp, _fp, _vp, _sz, _vp, _vp]),
     "aon_pos_enc": (_i, [_fp, _l, _i, _fp, _vp]),
     "aon_pos_enc_backward": (_i, [_fp, _fp, _l, _i, _fp, _vp]),
     "aon_composite": (_i, [_fp, _fp, _fp, _l, _fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _vp]),
@@ -167,6 +170,45 @@ def sample_along_rays(near: float, far: float, n_points: int, R: int, device, t_
     return t
 
 
+class AonRenderOpts(C.Structure):
+    """Mirror of `struct AonRenderOpts` in include/aon.h (per-call debugging / A-B knobs; the library keeps no switches)."""
+    _fields_ = [("force_segments", _i), ("no_tail_split", _i), ("no_fuse", _i), ("reserved", _i),
+                ("dbg", _vp), ("err_flag", _vp), ("timeline", _vp)]
+
+
+# Debug knobs live HERE (test / tool convenience), not in the C library: every render call passes them in an AonRenderOpts.
+_dbg = {"force_segments": 0, "no_tail_split": 0, "no_fuse": 0, "dbg": None, "err": None, "tl": None}
+
+
+def _opts():
+    if not any(_dbg.values()):
+        return None
+    o = AonRenderOpts()
+    o.force_segments, o.no_tail_split, o.no_fuse = int(_dbg["force_segments"]), int(_dbg["no_tail_split"]), int(_dbg["no_fuse"])
+    o.dbg = None if _dbg["dbg"] is None else _dbg["dbg"].data_ptr()
+    o.err_flag = None if _dbg["err"] is None else _dbg["err"].data_ptr()
+    o.timeline = None if _dbg["tl"] is None else _dbg["tl"].data_ptr()
+    return C.byref(o)
+
+
+_ws_cache = {}
+
+
+def workspace(device, precision: int, R: int) -> torch.Tensor:
+    """Caller-owned scratch for the render entry points (aon_workspace_bytes), cached per (device, stream) and grown on
+    demand; a uint8 CUDA tensor from torch's caching allocator."""
+    need = int(load().aon_workspace_bytes(precision, R))
+    if need == 0:
+        raise AonError("aon_workspace_bytes: bad precision %d" % precision)
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream())
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _ws_cache[key] = ws
+    return ws
+
+
 def render_level(kind: int, precision: int, packed: torch.Tensor, folded: Optional[torch.Tensor], rays_o, rays_d,
                  viewdirs, t_vals: torch.Tensor, white_bkgd: bool, want_weights: bool = True):
     """One level.  t_vals [S] (shared) or [R,S].  Returns (comp_rgb [R,3], acc [R], depth [R], weights [R,S]|None)."""
@@ -180,9 +222,11 @@ def render_level(kind: int, precision: int, packed: torch.Tensor, folded: Option
     depth = torch.empty(R, dtype=torch.float32, device=dev)
     w = torch.empty(R, S, dtype=torch.float32, device=dev) if want_weights else None
     with torch.cuda.device(dev):
+        ws = workspace(dev, precision, R)
         _check(lib.aon_render_level(kind, precision, packed.data_ptr(), _ptr(folded, "folded"), _ptr(rays_o, "rays_o"),
                                     _ptr(rays_d, "rays_d"), _ptr(viewdirs, "viewdirs"), _ptr(t_vals, "t_vals"), stride,
-                                    R, S, int(bool(white_bkgd)), _ptr(rgb), _ptr(acc), _ptr(depth), _ptr(w), _stream()),
+                                    R, S, int(bool(white_bkgd)), _ptr(rgb), _ptr(acc), _ptr(depth), _ptr(w), ws.data_ptr(),
+                                    ws.numel(), _opts(), _stream()),
                "aon_render_level")
     return rgb, acc, depth, w
 
@@ -200,6 +244,53 @@ def sample_pdf(t_coarse: torch.Tensor, weights: torch.Tensor, n_fine: int, u: Op
     return out
 
 
+def render_rays(kind: int, precision: int, packed_coarse, packed_fine, folded_coarse, folded_fine, rays_o, rays_d, viewdirs,
+                near: float, far: float, white_bkgd: bool, t_coarse: Optional[torch.Tensor] = None,
+                u: Optional[torch.Tensor] = None, want_coarse: bool = True):
+    """A8/A11: the whole coarse -> sample_pdf -> fine loop of NeRF.forward in one fused kernel (aon_render_rays).
+    Returns (fine [R,5], coarse [R,5] | None) with columns (r, g, b, acc, depth)."""
+    lib = load()
+    R = rays_o.shape[0]
+    dev = rays_o.device
+    out = torch.empty(R, 5, dtype=torch.float32, device=dev)
+    cout = torch.empty(R, 5, dtype=torch.float32, device=dev) if want_coarse else None
+    if t_coarse is not None and tuple(t_coarse.shape) != (R, 65):
+        raise AonError("render_rays: t_coarse must be [R,65]")
+    if u is not None and tuple(u.shape) != (R, 128):
+        raise AonError("render_rays: u must be [R,128]")
+    with torch.cuda.device(dev):
+        ws = workspace(dev, precision, R)
+        _check(lib.aon_render_rays(kind, precision, packed_coarse.data_ptr(), packed_fine.data_ptr(), _ptr(folded_coarse, "folded"),
+                                   _ptr(folded_fine, "folded"), _ptr(rays_o, "rays_o"), _ptr(rays_d, "rays_d"),
+                                   _ptr(viewdirs, "viewdirs"), _ptr(t_coarse, "t_coarse"), _ptr(u, "u"), R, float(near), float(far),
+                                   int(bool(white_bkgd)), _ptr(out), _ptr(cout), ws.data_ptr(), ws.numel(), _opts(), _stream()),
+               "aon_render_rays")
+    return out, cout
+
+
+def render_image(kind: int, precision: int, packed_coarse, packed_fine, folded_coarse, folded_fine, c2w, focal: float,
+                 H: int, W: int, near: float, far: float, white_bkgd: bool, ray0: int = 0, R: Optional[int] = None,
+                 want_coarse: bool = False, out: Optional[torch.Tensor] = None):
+    """A1+A2 + A8/A11: pixels [ray0, ray0 + R) of the H x W view of camera c2w, ray generation fused into the render
+    kernel (aon_render_image).  Returns (fine [R,5], coarse [R,5] | None)."""
+    lib = load()
+    if R is None:
+        R = H * W - ray0
+    dev = packed_coarse.device
+    c = torch.as_tensor(c2w, dtype=torch.float32).reshape(-1)[:12].cpu().contiguous()
+    arr = (C.c_float * 12)(*c.tolist())
+    if out is None:
+        out = torch.empty(R, 5, dtype=torch.float32, device=dev)
+    cout = torch.empty(R, 5, dtype=torch.float32, device=dev) if want_coarse else None
+    with torch.cuda.device(dev):
+        ws = workspace(dev, precision, R)
+        _check(lib.aon_render_image(kind, precision, packed_coarse.data_ptr(), packed_fine.data_ptr(), _ptr(folded_coarse, "folded"),
+                                    _ptr(folded_fine, "folded"), arr, float(focal), H, W, int(ray0), R, float(near), float(far),
+                                    int(bool(white_bkgd)), _ptr(out), _ptr(cout), ws.data_ptr(), ws.numel(), _opts(), _stream()),
+               "aon_render_image")
+    return out, cout
+
+
 def render_image_host(kind: int, precision: int, packed_coarse, packed_fine, folded_coarse, folded_fine,
                       rays_o: torch.Tensor, rays_d: torch.Tensor, viewdirs: torch.Tensor, near: float, far: float,
                       white_bkgd: bool, out: Optional[torch.Tensor] = None, coarse_out: Optional[torch.Tensor] = None):
@@ -213,11 +304,13 @@ def render_image_host(kind: int, precision: int, packed_coarse, packed_fine, fol
         out = torch.empty(R, 5, dtype=torch.float32).pin_memory()
     dev = packed_coarse.device
     with torch.cuda.device(dev):
+        ws = workspace(dev, precision, R)
         _check(lib.aon_render_image_host(kind, precision, packed_coarse.data_ptr(), packed_fine.data_ptr(),
                                          _ptr(folded_coarse, "folded"), _ptr(folded_fine, "folded"),
                                          rays_o.data_ptr(), rays_d.data_ptr(), viewdirs.data_ptr(), R, float(near),
                                          float(far), int(bool(white_bkgd)), out.data_ptr(),
-                                         None if coarse_out is None else coarse_out.data_ptr(), _stream()),
+                                         None if coarse_out is None else coarse_out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         _opts(), _stream()),
                "aon_render_image_host")
     return out
 
@@ -449,37 +542,30 @@ def debug_program_info(kind: int, precision: int) -> dict:
 
 
 def debug_set_buffers(dbg: Optional[torch.Tensor], err: Optional[torch.Tensor]) -> None:
-    """dbg: CUDA float32 [n_units,128,128] receiving the pre-activation outputs of every unit for ray
-    tile 0 / sample 0 of subsequent tensor-core render_level calls; err: CUDA int32 [1] receiving a code
+    """dbg: CUDA float32 [n_units,128,256] receiving the pre-activation outputs of every unit for ray
+    tile 0 / sample 0 of subsequent tensor-core render calls; err: CUDA int32 [1] receiving a code
     if a pipeline barrier times out.  Pass None, None to switch both off."""
-    lib = load()
-    lib.aon_debug_set_buffers.restype = None
-    lib.aon_debug_set_buffers.argtypes = [_vp, _vp]
-    lib.aon_debug_set_buffers(None if dbg is None else dbg.data_ptr(), None if err is None else err.data_ptr())
+    _dbg["dbg"], _dbg["err"] = dbg, err
 
 
 def debug_set_timeline(tl: Optional[torch.Tensor]) -> None:
     """tl: CUDA int64 [3,4,18,4] receiving SM-clock timestamps of pipeline events of CTA 0 (roles: MMA
     issuer, epilogue warp 0, encoder warp 0; first 4 samples; per unit; 4 events)."""
-    lib = load()
-    lib.aon_debug_set_timeline.restype = None
-    lib.aon_debug_set_timeline.argtypes = [_vp]
-    lib.aon_debug_set_timeline(None if tl is None else tl.data_ptr())
+    _dbg["tl"] = tl
 
 
 def debug_force_segments(n: int) -> None:
     """n > 0: every tensor-core render_level call cuts each ray's sample range into n segments (one CTA pair per ray tile
-    and segment, partial composites folded by a combine kernel); 0: automatic choice (small ray batches only)."""
-    lib = load()
-    lib.aon_debug_force_segments.restype = None
-    lib.aon_debug_force_segments.argtypes = [_i]
-    lib.aon_debug_force_segments(int(n))
+    and segment, per-sample (alpha, rgb) composited in order by a second kernel); 0: automatic choice."""
+    _dbg["force_segments"] = int(n)
 
 
 def debug_no_tail_split(on: bool) -> None:
-    """True: large ray batches are rendered by ONE unsplit launch per level (the behaviour before the last, partly filled
-    wave of ray tiles got its own sample-segmented launch).  For A/B timing and parity tests only."""
-    lib = load()
-    lib.aon_debug_no_tail_split.restype = None
-    lib.aon_debug_no_tail_split.argtypes = [_i]
-    lib.aon_debug_no_tail_split(1 if on else 0)
+    """True: large ray batches are rendered by ONE unsplit launch (the last, partly filled wave of ray tiles does not get
+    its own sample-segmented pass).  For A/B timing and parity tests only."""
+    _dbg["no_tail_split"] = 1 if on else 0
+
+
+def debug_no_fuse(on: bool) -> None:
+    """True: render_rays / render_image take the three-launch path (coarse level, sample_pdf, fine level) for every ray."""
+    _dbg["no_fuse"] = 1 if on else 0

@@ -7,8 +7,8 @@ Same class names, constructor defaults, ``forward`` signatures, return structure
 * ``NeRFMLP_AE`` / ``NeRF_AE_Art``  <- models/vanilla_nerf/model_autodecoder.py:60-337
 * ``CodeLibraryArticulated``        <- models/code_library.py:12-71
 
-``forward`` under ``torch.no_grad()`` (validation / ``--run_eval``) runs entirely in the fused CUDA
-kernels.  When gradients are required (``training_step``) the level is evaluated stage by stage so that it can be
+``forward`` under ``torch.no_grad()`` (validation / ``--run_eval``) is ONE fused CUDA kernel launch per call
+(``aon_render_rays``: coarse level, hierarchical sampling and fine level; outputs are column views of two [R,5] tensors).  When gradients are required (``training_step``) the level is evaluated stage by stage so that it can be
 differentiated: sampling, positional encoding and activations + compositing run in our kernels with
 hand-written adjoints (csrc/train_ops.cu); the vanilla MLP's contractions -- forward, dgrad and wgrad -- run as tcgen05
 GEMMs (csrc/gemm_tc.cu via train_tc.py; ``train_gemm = "torch"`` selects library GEMMs under autograd instead, which is
@@ -265,9 +265,9 @@ class _LevelLoop(nn.Module):
             if u is None:
                 u = torch.rand(R, self.num_fine_samples, device=dev)
             t0 = L.sample_along_rays(near, far, nc, R, dev, t_rand=t_rand.contiguous())
-        else:
-            t0 = L.sample_along_rays(near, far, nc, R, dev)
         if need_grad:
+            if not randomized:
+                t0 = L.sample_along_rays(near, far, nc, R, dev)
             return self._render_autograd(o, d, v, t0, u, white_bkgd, latents)
         kind = self.coarse_mlp.KIND
         pc = self._cache["coarse"].get(self.coarse_mlp, self.precision)
@@ -278,10 +278,10 @@ class _LevelLoop(nn.Module):
                     latents["articulation"].detach().float().contiguous())
             fc = L.fold_latents(kind, self.precision, pc, *args)
             ff = L.fold_latents(kind, self.precision, pf, *args)
-        rgb0, acc0, depth0, w0 = L.render_level(kind, self.precision, pc, fc, o, d, v, t0, white_bkgd, True)
-        t1 = L.sample_pdf(t0, w0, self.num_fine_samples, u=None if u is None else u.contiguous())
-        rgb1, acc1, depth1, _ = L.render_level(kind, self.precision, pf, ff, o, d, v, t1, white_bkgd, False)
-        return [(rgb0, acc0, depth0), (rgb1, acc1, depth1)]
+        # the whole level loop (coarse level, hierarchical sampling, fine level) is ONE fused kernel launch
+        fine, coarse = L.render_rays(kind, self.precision, pc, pf, fc, ff, o, d, v, near, far, white_bkgd,
+                                     t_coarse=t0 if randomized else None, u=None if u is None else u.contiguous())
+        return [(coarse[:, :3], coarse[:, 3], coarse[:, 4]), (fine[:, :3], fine[:, 3], fine[:, 4])]
 
     def _render_autograd(self, o, d, v, t0, u, white_bkgd, latents):
         R = o.shape[0]

@@ -12,10 +12,12 @@
  *   - every function returns 0 on success or a negative AON_E_* code; it never throws, exits or
  *     prints.  aon_last_error() returns a thread-local message for the last failure.
  *   - all tensor pointers are DEVICE pointers to contiguous row-major fp32 unless the name ends in
- *     _host; the caller allocates everything (no hidden allocation, no global mutable state);
- *     the one exception is aon_render_image_host(), which owns a scratch arena it creates lazily.
+ *     _host; the caller allocates everything (no hidden allocation, no global mutable state).
  *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*; NULL = legacy
  *     default stream); no entry point synchronises unless it says so.
+ *   - scratch memory is the CALLER's: entry points that need it take (workspace, workspace_bytes), sized by
+ *     aon_workspace_bytes(); the library never allocates device memory and keeps no global switches
+ *     (per-call knobs travel in AonRenderOpts).
  *   - the device is the calling thread's current CUDA device.
  */
 #ifndef AON_H_
@@ -28,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AON_ABI_VERSION 1
+#define AON_ABI_VERSION 2
 
 /* error codes */
 #define AON_OK 0
@@ -95,39 +97,87 @@ int aon_raygen(int H, int W, float focal, const float* c2w_host, float* rays_o, 
 int aon_sample_along_rays(float near, float far, int n_points, const float* t_rand, int R,
                           float* t_vals, aon_stream_t stream);
 
+/* ---- workspace + per-call options ---------------------------------------------------------------------
+ * aon_workspace_bytes: bytes of device scratch (256-byte aligned) that aon_render_level / aon_render_rays /
+ * aon_render_image / aon_render_image_host need for up to R rays in `precision`; 0 for a bad precision.
+ * It covers: the per-CTA scratch slots of the fused image kernel (coarse weights + fine sample positions of the
+ * CTA's 128 rays, L2-resident, 160 slots x 132 KB), the per-sample (alpha, rgb) buffer of sample-segmented
+ * launches (small ray batches, the last partial wave of a large one), the intermediates of the three-launch path
+ * those rays take, and device staging for the _host call.
+ * AonRenderOpts: optional per-call knobs for debugging and A/B timing; NULL = defaults.  Nothing is sticky. */
+size_t aon_workspace_bytes(int precision, int R);
+typedef struct AonRenderOpts {
+  int force_segments;   /* > 0: aon_render_level cuts every ray's sample range into this many segments              */
+  int no_tail_split;    /* 1: do not render the last partial wave of ray tiles in a separate, sample-segmented pass */
+  int no_fuse;          /* 1: aon_render_rays / _image take the three-launch path (coarse, sample_pdf, fine)        */
+  int reserved;
+  float* dbg;           /* device [n_units][128][256]: pre-activation output of every GEMM unit, tile 0 / sample 0  */
+  int* err_flag;        /* device int: receives a code if a pipeline barrier ever times out                          */
+  long long* timeline;  /* device [3][4][18][4]: SM-clock stamps of the pipeline roles of CTA 0                      */
+} AonRenderOpts;
+
 /* ---- A4+A5/A9+A6  one level: encode, MLP, activations, alpha compositing ---------------------------
  * Replaces, per level, cast_rays + pos_enc + NeRFMLP.forward + activations + volumetric_rendering
  * (helper.py:25-26,136-140,157-195; model.py:95-120,174-195; model_autodecoder.py:171-239,306-331).
  * t_vals: [R,S] (t_stride = S) or a shared table [S] (t_stride = 0).
  * folded: from aon_fold_latents() (auto-decoder) or NULL (vanilla).
- * Outputs: comp_rgb [R,3], acc [R], depth [R]; weights [R,S] may be NULL. */
+ * Outputs: comp_rgb [R,3], acc [R], depth [R]; weights [R,S] may be NULL.
+ * workspace may be NULL (small ray batches then run unsegmented: same values, lower occupancy). */
 int aon_render_level(int kind, int precision, const void* packed, const float* folded,
                      const float* rays_o, const float* rays_d, const float* viewdirs,
                      const float* t_vals, long t_stride, int R, int S, int white_bkgd,
-                     float* comp_rgb, float* acc, float* depth, float* weights,
-                     aon_stream_t stream);
+                     float* comp_rgb, float* acc, float* depth, float* weights, void* workspace,
+                     size_t workspace_bytes, const AonRenderOpts* opts, aon_stream_t stream);
 
 /* ---- A7  hierarchical sampling ------------------------------------------------------------------
  * Replaces the t_mids / weights[...,1:-1] slicing (model.py:162-166) + sample_pdf
  * (helper.py:203-252): t_coarse [R,n_coarse] (stride 0 = shared table), weights [R,n_coarse]
  * (the full compositing weights; the kernel drops the first and last itself),
  * u [R,n_fine] or [n_fine] (u_stride 0) or NULL = the reference's deterministic linspace;
- * t_fine [R, n_coarse+n_fine] sorted.  n_coarse <= 65, n_fine <= 128. */
+ * t_fine [R, n_coarse+n_fine] sorted.  n_coarse <= 65, n_fine <= 128.
+ * The 63-term weight sum follows ATen's CPU reduction order (see csrc/sampling.cuh), so t_fine is bit-equal
+ * to the reference's on the same weights. */
 int aon_sample_pdf(const float* t_coarse, long t_stride, const float* weights, const float* u,
                    long u_stride, int R, int n_coarse, int n_fine, float* t_fine,
                    aon_stream_t stream);
 
+/* ---- A8/A11  the whole level loop of NeRF.forward in ONE kernel ---------------------------------------
+ * Replaces NeRF.forward / NeRF_AE_Art.forward (model.py:147-199; model_autodecoder.py:278-337) and the
+ * chunk loop of render_rays / render_rays_test around it (model.py:295-348; model_autodecoder.py:479-541):
+ * coarse level (65 samples), hierarchical sampling, fine level (193 samples) of every ray inside one fused
+ * kernel launch -- each CTA keeps the coarse weights and fine sample positions of its 128 rays in an
+ * L2-resident scratch slot, so no [rays x samples] tensor is written to HBM.
+ *   t_coarse  NULL = deterministic coarse table (eval); else [R,65] per-ray positions (randomized training draws)
+ *   u         NULL = deterministic inverse-cdf table; else [R,128] uniform draws
+ *   out       [R,5] = (r, g, b, acc, depth) of the fine level;  coarse_out [R,5] of the coarse level or NULL
+ * Rays beyond the last full wave of CTA pairs (and whole batches smaller than one wave) take a
+ * sample-segmented three-launch path through the workspace; results do not depend on the split. */
+int aon_render_rays(int kind, int precision, const void* packed_coarse, const void* packed_fine,
+                    const float* folded_coarse, const float* folded_fine, const float* rays_o,
+                    const float* rays_d, const float* viewdirs, const float* t_coarse, const float* u,
+                    int R, float near, float far, int white_bkgd, float* out, float* coarse_out,
+                    void* workspace, size_t workspace_bytes, const AonRenderOpts* opts,
+                    aon_stream_t stream);
+
+/* Same, with ray generation (A1+A2; datasets/ray_utils.py:71-90,118-159) fused in: renders pixels
+ * [ray0, ray0 + R) (row-major) of the H x W view of camera c2w_host (12 floats, [3,4] row-major, read on
+ * the host at call time).  ray0 / R let N ranks render contiguous pixel blocks of one image. */
+int aon_render_image(int kind, int precision, const void* packed_coarse, const void* packed_fine,
+                     const float* folded_coarse, const float* folded_fine, const float* c2w_host,
+                     float focal, int H, int W, long ray0, int R, float near, float far,
+                     int white_bkgd, float* out, float* coarse_out, void* workspace,
+                     size_t workspace_bytes, const AonRenderOpts* opts, aon_stream_t stream);
+
 /* ---- A8/A11  whole-image render from HOST buffers ----------------------------------------------
- * Replaces render_rays / render_rays_test's chunk loop over NeRF.forward (model.py:295-348;
- * model_autodecoder.py:479-541) for deterministic eval: host rays in, host pixels out.  Does
- * H2D copies, coarse level, sample_pdf, fine level, D2H copies on `stream` and SYNCHRONISES it.
- * rays_*_host [R,3]; out_host [R,5] = (r,g,b,acc,depth) of the FINE level;
- * coarse_out_host [R,5] may be NULL.  packed_coarse/fine + folded_* are device pointers. */
+ * aon_render_rays with HOST rays in and HOST pixels out: H2D copies, the fused render, D2H copies on
+ * `stream`, then SYNCHRONISES it.  rays_*_host [R,3]; out_host [R,5] = (r,g,b,acc,depth) of the FINE
+ * level; coarse_out_host [R,5] may be NULL.  packed_* / folded_* / workspace are device pointers. */
 int aon_render_image_host(int kind, int precision, const void* packed_coarse,
                           const void* packed_fine, const float* folded_coarse,
                           const float* folded_fine, const float* rays_o_host,
                           const float* rays_d_host, const float* viewdirs_host, int R, float near,
                           float far, int white_bkgd, float* out_host, float* coarse_out_host,
+                          void* workspace, size_t workspace_bytes, const AonRenderOpts* opts,
                           aon_stream_t stream);
 
 /* ---- training path, stage 1: per-element stages with hand-written adjoints ------------

@@ -26,7 +26,7 @@ def test_header_symbols_exported(built_lib):
 
 def test_introspection(built_lib):
     lib = built_lib.load()
-    assert lib.aon_version() == 1
+    assert lib.aon_version() == 2
     assert lib.aon_num_layers(0) == 12 and lib.aon_num_layers(1) == 20 and lib.aon_num_layers(7) < 0
     from oracle import ref_cpu as O
     assert built_lib.layer_shapes(0) == [(o, i) for _, o, i in O.VANILLA_LAYERS]
@@ -38,12 +38,28 @@ def test_introspection(built_lib):
 
 def test_argument_errors_return_codes(built_lib):
     lib = built_lib.load()
-    rc = lib.aon_render_level(0, 0, None, None, None, None, None, None, 0, 1, 65, 1, None, None, None, None, None)
+    rc = lib.aon_render_level(0, 0, None, None, None, None, None, None, 0, 1, 65, 1, None, None, None, None, None, 0, None, None)
     assert rc == -1 and b"null" in lib.aon_last_error()
     rc = lib.aon_sample_pdf(None, 0, None, None, 0, 1, 65, 128, None, None)
     assert rc == -1
     rc = lib.aon_raygen(0, 0, ctypes.c_float(1.0), None, None, None, None)
     assert rc == -1
+    rc = lib.aon_render_rays(0, 1, None, None, None, None, None, None, None, None, None, 4, 2.0, 6.0, 1, None, None, None, 0, None, None)
+    assert rc == -1 and b"null" in lib.aon_last_error()
+    rc = lib.aon_render_image(0, 1, None, None, None, None, None, 100.0, 4, 4, 0, 16, 2.0, 6.0, 1, None, None, None, 0, None, None)
+    assert rc == -1 and b"camera" in lib.aon_last_error()
+
+
+def test_workspace_contract(built_lib):
+    """The caller owns all scratch: aon_workspace_bytes is monotone in R, covers the fused kernel's scratch slots in the
+    tensor-core modes, and rejects bad precisions; the options struct mirror has the documented size."""
+    lib = built_lib.load()
+    assert lib.aon_workspace_bytes(99, 10) == 0
+    a, b, c = lib.aon_workspace_bytes(1, 1), lib.aon_workspace_bytes(1, 3840), lib.aon_workspace_bytes(1, 307200)
+    assert 0 < a <= b <= c
+    assert a >= 160 * 128 * (65 + 193) * 4                     # scratch slots of the fused kernel
+    assert lib.aon_workspace_bytes(0, 3840) >= 3840 * (65 + 193) * 4
+    assert ctypes.sizeof(built_lib.AonRenderOpts) == 40
 
 
 def test_sass_is_sm100a(built_lib):

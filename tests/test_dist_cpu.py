@@ -26,13 +26,16 @@ def _worker(rank, ws, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=ws)
     from aon_b200 import dist as D
     ok = True
-    for R in (1, 127, 128, 129, 1000, 4097):
+    for R in (1, 127, 128, 129, 512, 1000, 4097):
         rays = _rays(R)
         full = _fake_render(rays)
         got = D.render_sharded(_fake_render, rays)
         ok &= got.shape == full.shape and torch.equal(got, full)
         got0 = D.render_sharded(_fake_render, rays, gather="rank0")
         ok &= (got0 is None) if rank else torch.equal(got0, full)
+        # camera form (the fused image kernel generates its own rays: blocks are addressed by pixel range)
+        goti = D.render_image_sharded(lambda lo, hi: full[lo:hi].clone(), R)
+        ok &= goti.shape == full.shape and torch.equal(goti, full)
     g = torch.full((1000,), float(rank + 1))
     D.allreduce_mean_(g)
     ok &= torch.allclose(g, torch.full((1000,), (1 + ws) / 2.0 * 1.0))

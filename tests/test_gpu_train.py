@@ -7,6 +7,8 @@
 * end to end: parameter gradients of loss0 + loss1 of a randomized training batch through nerf.NeRF / NeRF_AE_Art
   (native sampling, pos_enc, compositing + library GEMMs) vs autograd of the oracle on the CPU with the same random draws.
 Tolerances are written at each assert."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -171,6 +173,59 @@ def test_training_gradients_match_oracle_autograd(built_lib, kind, sharp):
     # the tcgen05 training GEMMs carry 22-bit (fp16 hi+lo) operands: ~4x the rounding noise of fp32 operands, so in the
     # chaotic (sharp density) cases our distance from fp64 is a small multiple of the fp32 reference's own distance
     assert ours < max(2e-4, 8 * floor), (ours, floor, worst)
+
+
+@pytest.mark.parametrize("kind", ["vanilla", "autodecoder"])
+def test_training_gradients_vs_reference_golden(built_lib, kind, golden_dir):
+    """tests/golden/train_*.npz hold a randomized batch (rays, target, the stratified / inverse-cdf draws) together with the
+    loss and the parameter gradients the UNMODIFIED reference's autograd produced for it (oracle/gen_golden_train.py).
+    The CUDA training path (nerf.NeRF / NeRF_AE_Art under grad: tcgen05 forward / dgrad / wgrad GEMMs + hand-written
+    adjoints) must reproduce them: loss to 1e-5 relative, every gradient's sum of magnitudes and the stored whole
+    gradients to a bar tied to the reference's own fp32-vs-fp64 distance on this batch (sharp densities, see above)."""
+    import numpy as np
+    from aon_b200 import nerf
+    g = np.load(os.path.join(golden_dir, "train_%s_sharp_R33.npz" % kind))
+    T = lambda k: torch.from_numpy(np.asarray(g[k]))
+    sd = O.make_state_dict(kind, 0, sharp=True)
+    net = _make_net(nerf, kind, sd, torch.device(DEV)).train()
+    rays = {k: T(k) for k in ("rays_o", "rays_d", "viewdirs")}
+    target, t_rand, u = T("target"), T("t_rand"), T("u")
+    _, g32 = _oracle_grads(sd, kind, rays, target, t_rand, u, torch.float32)
+    loss64, g64 = _oracle_grads(sd, kind, rays, target, t_rand, u, torch.float64)
+    floor = max(_rel(g32[n], g64[n], floor=1e-9) for n in g64)
+    lat_d = None
+    if kind == "autodecoder":
+        lat = O.code_library(sd, torch.tensor([0]), torch.tensor([3]))
+        lat_d = {k: v.detach().to(DEV).requires_grad_(True) for k, v in lat.items()}
+    rd = {k: v.to(DEV) for k, v in rays.items()}
+    args = (rd, True, True, 2.0, 6.0) + ((lat_d,) if lat_d is not None else ())
+    got = net(*args, t_rand=t_rand.to(DEV), u=u.to(DEV))
+    loss = nerf.img2mse(got[0][0], target.to(DEV)) + nerf.img2mse(got[1][0], target.to(DEV))
+    loss.backward()
+    ref_loss = float(g["loss"])
+    assert abs(loss.item() - ref_loss) < max(1e-5 * abs(ref_loss), 5 * abs(ref_loss - loss64)), (loss.item(), ref_loss)
+    grads = {n: prm.grad.cpu() for n, prm in net.named_parameters()}
+    if lat_d is not None:
+        pre = "code_library.embedding_instance_"
+        for k, full, row in (("density", pre + "shape.weight", 0), ("color", pre + "appearance.weight", 0),
+                             ("articulation", pre + "articulation.weight", 3)):
+            grads[full] = torch.zeros_like(sd[full])
+            grads[full][row] = lat_d[k].grad[0].cpu()
+    names = [str(n) for n in g["grad_names"]]
+    assert set(names) == set(grads)
+    tol = max(2e-4, 8 * floor)
+    for n, want in zip(names, g["grad_abs_sums"]):               # every reference gradient, by its sum of magnitudes
+        have = grads[n].double().abs().sum().item()
+        assert abs(have - float(want)) <= tol * max(float(want), 1e-12), (n, have, float(want), tol)
+    checked = 0
+    for key in g.files:                                          # the whole gradients the golden stores
+        if key.startswith("grad/"):
+            e = _rel(grads[key[5:]], T(key), floor=1e-9)
+            assert e < tol, (key, e, tol)
+            checked += 1
+    assert checked >= 4
+    print("golden training batch %s: loss %.8f (reference %.8f), %d gradients, bar %.2e (fp32 floor %.2e)"
+          % (kind, loss.item(), ref_loss, len(names), tol, floor))
 
 
 def test_flat_adam_training_updates_packed_weights(built_lib):
