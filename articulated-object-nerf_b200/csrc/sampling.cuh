@@ -103,15 +103,16 @@ __device__ __forceinline__ void sample_pdf_ray(const float* __restrict__ tc, con
   const float padw = __fdiv_rn(padding, (float)nw);
   const float wsum = __fadd_rn(wsum0, padding);
   // cdf[0]=0, cdf[k]=min(1, cumsum(pdf)[k-1]) for k=1..nw-1, cdf[nw]=1   (nw+1 = nb entries)
-  // pdf in parallel, then the sequential fp32 cumsum of torch.cumsum (CPU) by lane 0 (62 adds).
+  // pdf in parallel, then torch.cumsum's CPU algorithm by lane 0: a sequential scan whose running sum is a DOUBLE
+  // (ATen ReduceOpsKernel.cpp cumsum_cpu_kernel: at::acc_type<float, false> = double) rounded to fp32 per element.
   for (int k = lane; k < nw - 1; k += 32) sc[k + 1] = __fdiv_rn(__fadd_rn(sw[k], padw), wsum);
   __syncwarp();
   if (lane == 0) {
-    float c = 0.f;
+    double c = 0.0;
     sc[0] = 0.f;
     for (int k = 0; k < nw - 1; ++k) {
-      c = __fadd_rn(c, sc[k + 1]);
-      sc[k + 1] = fminf(1.0f, c);
+      c += (double)sc[k + 1];
+      sc[k + 1] = fminf(1.0f, (float)c);
     }
     sc[nw] = 1.0f;
   }

@@ -59,7 +59,13 @@ class LitModel(nn.Module):
 
     @torch.no_grad()
     def psnr_legacy(self, pred: Tensor, gt: Tensor) -> Tensor:
-        """interface.py:54-62: clip to [0,1], -10 log10(mse)."""
+        """interface.py:72-74: -10 log10(mean((pred - gt)^2)), NOT clipped (the validation logs use this one; the
+        auto-decoder's padded sigmoid leaves rgb in [-0.001, 1.001])."""
+        return -10.0 * torch.log10(torch.mean((pred - gt) ** 2))
+
+    @torch.no_grad()
+    def psnr_clipped(self, pred: Tensor, gt: Tensor) -> Tensor:
+        """interface.py:54-62 (psnr_each): clip both images to [0,1] first, then -10 log10(mse)."""
         mse = torch.mean((torch.clip(pred, 0, 1) - torch.clip(gt, 0, 1)) ** 2)
         return -10.0 * torch.log(mse) / np.log(10)
 
@@ -186,7 +192,7 @@ class _LitCommon(LitModel):
     # ---- evaluation artefacts (model.py:459-507; interface.py:64-99,125-138) ----
     @torch.no_grad()
     def psnr_each(self, preds, gts):
-        return torch.stack([self.psnr_legacy(p, g) for p, g in zip(preds, gts)])
+        return torch.stack([self.psnr_clipped(p, g) for p, g in zip(preds, gts)])
 
     @torch.no_grad()
     def psnr(self, preds, gts, i_train=None, i_val=None, i_test=None, name="PSNR"):
@@ -334,11 +340,24 @@ class Trainer:
         self.max_steps, self.log_every = max_steps, log_every
         self.global_step = 0
         self.is_global_zero = D.world()[0] == 0
+        self.ckpt_every, self.on_checkpoint = 0, None     # periodic checkpoints (run.py sets both on rank 0)
+
+    def resume(self, system: "_LitCommon", blob: dict) -> None:
+        """Continue a run from a checkpoint written by run.save_checkpoint: the step count (LR warm-up / decay position)
+        and the Adam moments + bias-correction step.  The weights were loaded by the caller (load_state_dict)."""
+        self.global_step = int(blob.get("global_step", 0))
+        states = blob.get("optimizer_states") or []
+        if states:
+            opt = getattr(system, "_optimizer", None) or system.configure_optimizers()
+            opt.load_state_dict(states[0])
+            system._optimizer = opt
+            system._resumed = True
 
     def fit(self, system: _LitCommon, batches) -> _LitCommon:
         system.trainer = self
         opt = getattr(system, "_optimizer", None) or system.configure_optimizers()
-        if getattr(system, "_optimizer", None) is None and D.world()[1] > 1:
+        if (getattr(system, "_optimizer", None) is None or getattr(system, "_resumed", False)) and D.world()[1] > 1:
+            system._resumed = False
             torch.distributed.broadcast(opt.flat, src=0)     # DDP start state: every rank trains rank 0's initial weights
             for p in opt.param_groups[0]["params"]:
                 torch.autograd.graph.increment_version(p)    # the packed-weight cache keys on parameter versions
@@ -356,6 +375,8 @@ class Trainer:
             self.global_step += 1
             if self.log_every and self.is_global_zero and self.global_step % self.log_every == 0:
                 print("step %d  %s" % (self.global_step, {k: round(v, 4) for k, v in system.logged.items()}), flush=True)
+            if self.ckpt_every and self.on_checkpoint is not None and self.global_step % self.ckpt_every == 0:
+                self.on_checkpoint(self.global_step)
         return system
 
     @torch.no_grad()
