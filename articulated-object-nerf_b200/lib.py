@@ -181,7 +181,7 @@ _dbg = {"force_segments": 0, "no_tail_split": 0, "no_fuse": 0, "dbg": None, "err
 
 
 def _opts():
-    if not any(_dbg.values()):
+    if not any((v is not None) if not isinstance(v, int) else (v != 0) for v in _dbg.values()):
         return None
     o = AonRenderOpts()
     o.force_segments, o.no_tail_split, o.no_fuse = int(_dbg["force_segments"]), int(_dbg["no_tail_split"]), int(_dbg["no_fuse"])
