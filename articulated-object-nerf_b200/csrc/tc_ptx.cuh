@@ -71,6 +71,23 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// One lane of a fully converged warp (elect.sync).  The control roles run with the WHOLE warp converged and only the
+// elected lane executes the tcgen05 / bulk-copy instructions: the compiler then knows the operands are warp-uniform and keeps
+// them in uniform registers.  A role written as `if (lane == 0) {...}` makes every operand "divergent": each UTCHMMA / UBLKCP
+// was wrapped in an ELECT + 5 x R2UR.BROADCAST + branch waterfall loop (seen in the SASS of the round-1 kernel), ~100 cycles
+// per instruction on the critical issue path.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- async proxy ---------------------------------------------------------------------------------
 // generic-proxy st.shared -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
