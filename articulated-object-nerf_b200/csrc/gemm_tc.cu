@@ -11,12 +11,20 @@
 // Weights are packed per step into PW(rows, contraction) = [contraction/8][rows][8] (K-major B operand), once as W
 // (forward) and once as W^T (dgrad).
 //
-// One CTA = one 128 x N output tile (N <= 256): warp 0 = producer (bulk copies global -> 2-stage shared-memory ring,
-// mbarrier complete_tx), warp 1 = MMA issuer (one elected thread, tcgen05.mma cta_group::1 kind::f16, tcgen05.commit
-// releases ring slots / publishes the accumulator), warps 2-5 = epilogue (tcgen05.ld, bias / ReLU / ReLU-mask, pack to
+// One CTA = one 128 x N output tile (N <= 256): warp 0 = producer (TMA global -> 2-stage shared-memory ring, mbarrier
+// complete_tx: the contiguous A block of forward / dgrad as one 1-D bulk copy, everything strided -- the weight rows of a K
+// chunk, the 32-sample slabs of both wgrad operands -- as ONE tensor-map box per plane), warp 1 = MMA issuer (tcgen05.mma
+// cta_group::1 kind::f16, tcgen05.commit releases ring slots / publishes the accumulator); both run as converged warps with
+// one elected lane executing the TMA / MMA instructions (operands stay in uniform registers), warps 2-5 = epilogue (tcgen05.ld, bias / ReLU / ReLU-mask, pack to
 // hi+lo, coalesced 16-byte stores).  96 KB of shared memory and <= 256 TMEM columns per CTA -> two CTAs per SM, so one
 // CTA's epilogue overlaps the other's MMAs.  wgrad CTAs loop over their share of the sample tiles (split-K) and write fp32
 // partial tiles that wgrad_reduce_kernel sums in a fixed order (deterministic).
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "aon_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -31,7 +39,15 @@ constexpr uint32_t GT_B_PLANE = 256 * GT_KC * 2;   // 16 KB: up to 256 rows
 constexpr uint32_t GT_STAGE = 2 * GT_A_PLANE + 2 * GT_B_PLANE;   // 48 KB
 constexpr uint32_t GT_SMEM = GT_NS * GT_STAGE + 1024;             // + alignment slack
 
-struct GtParams {
+// Tensor maps of the wgrad (TN) operands (CUtensorMap, 64-byte aligned, read from kernel parameter space): tm[plane] =
+// operand A, tm[2 + plane] = operand B.  A PK tensor [tiles][feat/8][128][8] x 16 bit is described in 8-byte elements as
+// {256, feat/8, tiles} (the 128 x 8 slab of a feature group is 2 KB contiguous); a stage's box {GT_KC * 2, groups, 1} takes
+// GT_KC samples (512 contiguous bytes) of `groups` feature groups and lands as [group][sample][8] -- one instruction instead
+// of 16 + N/8 separate 512-byte copies per plane.  (An inner box of 8 x 16-bit = 16 bytes moves the same bytes as hundreds of
+// 16-byte rows and is slower than the separate copies were: measured.)  Forward / dgrad (NT) operands are contiguous per K
+// chunk and stay 1-D bulk copies.
+struct alignas(64) GtParams {
+  CUtensorMap tm[4];
   AonGemm g;
 };
 
@@ -43,14 +59,15 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return (uint32_t)__half_as_ushort(__float2half_rn(a)) | ((uint32_t)__half_as_ushort(__float2half_rn(b)) << 16);
 }
 
-__global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P) {
+__global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const __grid_constant__ GtParams P) {
   extern __shared__ unsigned char gt_smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[2 * GT_NS + 1];
   __shared__ uint32_t s_tmem;
   __shared__ float s_colsum[4][256];     // per epilogue warp: column sums of its 32 rows (bias gradients)
   __shared__ float s_bias[256];
   const AonGemm& g = P.g;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: the control warps stay converged
   const uint32_t sm0 = (smem_u32(gt_smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = smem_u32(s_bar);
   auto full = [&](int s) { return bar0 + 8u * s; };
@@ -69,7 +86,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = s_tmem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem, 0);
 
   // ---- work decomposition -----------------------------------------------------------------------------------------
   // NT: blockIdx.x = row tile; stages = for each segment, K chunks of GT_KC.
@@ -85,8 +102,9 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
   else for (int sgi = 0; sgi < g.nseg; ++sgi) n_stage_total += (g.kext[sgi] + GT_KC - 1) / GT_KC;
 
   if (warp == 0) {
-    // ================= producer =================
+    // ================= producer (converged warp; one elected lane issues the copies) =================
     long it = 0;
+    const int planes = x3 ? 2 : 1;
     if (!tn) {
       const long tile = blockIdx.x;
       for (int sgi = 0; sgi < g.nseg; ++sgi) {
@@ -97,55 +115,46 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
           const int s = (int)(it % GT_NS);
           const int kc = min(GT_KC, g.kext[sgi] - k0), nkg = kc / 8;
           gt_wait(empty(s), (uint32_t)(((it / GT_NS) & 1) ^ 1));
-          const uint32_t a_bytes = (uint32_t)nkg * 2048u, b_piece = (uint32_t)N * 16u;
-          const int planes = x3 ? 2 : 1;
-          if (lane == 0) mbar_arrive_expect_tx(full(s), (uint32_t)planes * (a_bytes + (uint32_t)nkg * b_piece));
-          __syncwarp();
-          const uint32_t st = sm0 + (uint32_t)s * GT_STAGE;
-          // pieces: per plane 1 A block + nkg B row blocks
-          const int per_plane = 1 + nkg;
-          for (int p = lane; p < planes * per_plane; p += 32) {
-            const int pl = p / per_plane, q = p % per_plane;
-            if (q == 0) {
+          if (elect_one()) {
+            const uint32_t a_bytes = (uint32_t)nkg * 2048u, b_piece = (uint32_t)N * 16u;
+            mbar_arrive_expect_tx(full(s), (uint32_t)planes * (a_bytes + (uint32_t)nkg * b_piece));
+            const uint32_t st = sm0 + (uint32_t)s * GT_STAGE;
+            const bool whole_rows = g.b_row0[sgi] == 0 && N == g.b_feat[sgi];   // the k-groups of the chunk are contiguous
+            for (int pl = 0; pl < planes; ++pl) {
               bulk_g2s(st + (uint32_t)pl * GT_A_PLANE, a_pl[pl] + a_tile + (long)((g.a_off[sgi] + k0) / 8) * 2048, a_bytes, full(s));
-            } else {
-              const int kg = q - 1;
-              bulk_g2s(st + 2 * GT_A_PLANE + (uint32_t)pl * GT_B_PLANE + (uint32_t)kg * b_piece,
-                       b_pl[pl] + ((long)((g.b_off[sgi] + k0) / 8 + kg) * g.b_feat[sgi] + g.b_row0[sgi]) * 16, b_piece, full(s));
+              const char* bsrc = b_pl[pl] + ((long)((g.b_off[sgi] + k0) / 8) * g.b_feat[sgi] + g.b_row0[sgi]) * 16;
+              const uint32_t bdst = st + 2 * GT_A_PLANE + (uint32_t)pl * GT_B_PLANE;
+              if (whole_rows) {
+                bulk_g2s(bdst, bsrc, (uint32_t)nkg * b_piece, full(s));
+              } else {
+                for (int kg = 0; kg < nkg; ++kg) bulk_g2s(bdst + (uint32_t)kg * b_piece, bsrc + (long)kg * g.b_feat[sgi] * 16, b_piece, full(s));
+              }
             }
           }
         }
       }
     } else {
-      const char* a_pl[2] = {(const char*)g.a_hi[0], (const char*)g.a_lo[0]};
-      const char* b_pl[2] = {(const char*)g.b_hi[0], (const char*)g.b_lo[0]};
-      const int a_ng0 = g.a_off[0] / 8 + (int)blockIdx.x * 16, b_ng0 = g.b_off[0] / 8, b_ngn = N / 8;
-      const int planes = x3 ? 2 : 1, per_plane = 16 + b_ngn;
-      constexpr uint32_t PIECE = GT_KC * 16;     // 32 rows x 16 B
+      const int a_ng0 = g.a_off[0] / 8 + (int)blockIdx.x * 16, b_ng0 = g.b_off[0] / 8;
+      const uint32_t stage_bytes = (uint32_t)planes * (uint32_t)(16 + N / 8) * (GT_KC * 16u);
       for (int t = t_begin; t < t_end; ++t) {
         for (int q4 = 0; q4 < 128 / GT_KC; ++q4, ++it) {
           const int s = (int)(it % GT_NS);
           gt_wait(empty(s), (uint32_t)(((it / GT_NS) & 1) ^ 1));
-          if (lane == 0) mbar_arrive_expect_tx(full(s), (uint32_t)(planes * per_plane) * PIECE);
-          __syncwarp();
-          const uint32_t st = sm0 + (uint32_t)s * GT_STAGE;
-          for (int p = lane; p < planes * per_plane; p += 32) {
-            const int pl = p / per_plane, q = p % per_plane;
-            if (q < 16) {
-              bulk_g2s(st + (uint32_t)pl * GT_A_PLANE + (uint32_t)q * PIECE,
-                       a_pl[pl] + (((long)t * (g.a_feat[0] / 8) + a_ng0 + q) * 128 + q4 * GT_KC) * 16, PIECE, full(s));
-            } else {
-              const int ng = q - 16;
-              bulk_g2s(st + 2 * GT_A_PLANE + (uint32_t)pl * GT_B_PLANE + (uint32_t)ng * PIECE,
-                       b_pl[pl] + (((long)t * (g.b_feat[0] / 8) + b_ng0 + ng) * 128 + q4 * GT_KC) * 16, PIECE, full(s));
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full(s), stage_bytes);
+            const uint32_t st = sm0 + (uint32_t)s * GT_STAGE;
+            for (int pl = 0; pl < planes; ++pl) {
+              // 32 samples x 128 features of A and x N features of B: one box each, landing as [feature group][sample][8]
+              tma_load_3d(st + (uint32_t)pl * GT_A_PLANE, &P.tm[pl], q4 * (GT_KC * 2), a_ng0, t, full(s));
+              tma_load_3d(st + 2 * GT_A_PLANE + (uint32_t)pl * GT_B_PLANE, &P.tm[2 + pl], q4 * (GT_KC * 2), b_ng0, t, full(s));
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (converged warp; one elected lane issues) =================
+    {
       const uint32_t idesc = idesc_f16(128, N, 0) | (tn ? ((1u << 15) | (1u << 16)) : 0u);
       uint32_t accumulate = 0;
       long it = 0;
@@ -175,19 +184,25 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const GtParams P
             const int s = (int)(it % GT_NS);
             gt_wait(full(s), (uint32_t)((it / GT_NS) & 1));
             tc_fence_after();
-            issue_stage(s, min(GT_KC, g.kext[sgi] - k0));
-            mma_commit(empty(s));
+            if (elect_one()) {
+              issue_stage(s, min(GT_KC, g.kext[sgi] - k0));
+              mma_commit(empty(s));
+            }
+            accumulate = 1;
           }
       } else {
         for (; it < n_stage_total; ++it) {
           const int s = (int)(it % GT_NS);
           gt_wait(full(s), (uint32_t)((it / GT_NS) & 1));
           tc_fence_after();
-          issue_stage(s, GT_KC);
-          mma_commit(empty(s));
+          if (elect_one()) {
+            issue_stage(s, GT_KC);
+            mma_commit(empty(s));
+          }
+          accumulate = 1;
         }
       }
-      mma_commit(accum);
+      if (elect_one()) mma_commit(accum);
     }
   } else {
     // ================= epilogue (warps 2..5: TMEM lane quadrant = warp % 4) =================
@@ -344,14 +359,15 @@ constexpr int GP_THREADS = 64 + 32 * GP_EPI_WARPS;                 // 320
 constexpr int GP_EPI_THREADS = 32 * GP_EPI_WARPS;                  // 256
 constexpr uint32_t GP_SMEM = GP_NS * GT_STAGE + 1024;
 
-__global__ void __launch_bounds__(GP_THREADS, 1) gemm_tc_nt_persistent_kernel(const GtParams P) {
+__global__ void __launch_bounds__(GP_THREADS, 1) gemm_tc_nt_persistent_kernel(const __grid_constant__ GtParams P) {
   extern __shared__ unsigned char gt_smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[2 * GP_NS + 4];
   __shared__ uint32_t s_tmem;
   __shared__ float s_colsum[2][4][256];  // [tile parity][lane quadrant]: column sums of the quadrant's 32 rows (bias gradients)
   __shared__ float s_bias[256];
   const AonGemm& g = P.g;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const uint32_t sm0 = (smem_u32(gt_smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = smem_u32(s_bar);
   auto full = [&](int s) { return bar0 + 8u * s; };
@@ -371,11 +387,11 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_tc_nt_persistent_kernel(co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = s_tmem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem, 0);
   const long tile0 = blockIdx.x, tile_step = gridDim.x, tile_end = g.m_tiles;
 
   if (warp == 0) {
-    // ================= producer =================
+    // ================= producer (converged warp; one elected lane issues the copies) =================
     long it = 0;
     const int planes = x3 ? 2 : 1;
     for (long tile = tile0; tile < tile_end; tile += tile_step) {
@@ -387,27 +403,28 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_tc_nt_persistent_kernel(co
           const int s = (int)(it % GP_NS);
           const int kc = min(GT_KC, g.kext[sgi] - k0), nkg = kc / 8;
           gt_wait(empty(s), (uint32_t)(((it / GP_NS) & 1) ^ 1));
-          const uint32_t a_bytes = (uint32_t)nkg * 2048u, b_piece = (uint32_t)N * 16u;
-          if (lane == 0) mbar_arrive_expect_tx(full(s), (uint32_t)planes * (a_bytes + (uint32_t)nkg * b_piece));
-          __syncwarp();
-          const uint32_t st = sm0 + (uint32_t)s * GT_STAGE;
-          const int per_plane = 1 + nkg;
-          for (int p = lane; p < planes * per_plane; p += 32) {
-            const int pl = p / per_plane, q = p % per_plane;
-            if (q == 0) {
+          if (elect_one()) {
+            const uint32_t a_bytes = (uint32_t)nkg * 2048u, b_piece = (uint32_t)N * 16u;
+            mbar_arrive_expect_tx(full(s), (uint32_t)planes * (a_bytes + (uint32_t)nkg * b_piece));
+            const uint32_t st = sm0 + (uint32_t)s * GT_STAGE;
+            const bool whole_rows = g.b_row0[sgi] == 0 && N == g.b_feat[sgi];   // the k-groups of the chunk are contiguous
+            for (int pl = 0; pl < planes; ++pl) {
               bulk_g2s(st + (uint32_t)pl * GT_A_PLANE, a_pl[pl] + a_tile + (long)((g.a_off[sgi] + k0) / 8) * 2048, a_bytes, full(s));
-            } else {
-              const int kg = q - 1;
-              bulk_g2s(st + 2 * GT_A_PLANE + (uint32_t)pl * GT_B_PLANE + (uint32_t)kg * b_piece,
-                       b_pl[pl] + ((long)((g.b_off[sgi] + k0) / 8 + kg) * g.b_feat[sgi] + g.b_row0[sgi]) * 16, b_piece, full(s));
+              const char* bsrc = b_pl[pl] + ((long)((g.b_off[sgi] + k0) / 8) * g.b_feat[sgi] + g.b_row0[sgi]) * 16;
+              const uint32_t bdst = st + 2 * GT_A_PLANE + (uint32_t)pl * GT_B_PLANE;
+              if (whole_rows) {
+                bulk_g2s(bdst, bsrc, (uint32_t)nkg * b_piece, full(s));
+              } else {
+                for (int kg = 0; kg < nkg; ++kg) bulk_g2s(bdst + (uint32_t)kg * b_piece, bsrc + (long)kg * g.b_feat[sgi] * 16, b_piece, full(s));
+              }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (converged warp; one elected lane issues) =================
+    {
       const uint32_t idesc = idesc_f16(128, N, 0);
       long it = 0, lt = 0;
       for (long tile = tile0; tile < tile_end; tile += tile_step, ++lt) {
@@ -424,18 +441,22 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_tc_nt_persistent_kernel(co
             const uint32_t st = sm0 + (uint32_t)s * GT_STAGE;
             const uint32_t a_hi = st, a_lo = st + GT_A_PLANE, b_hi = st + 2 * GT_A_PLANE, b_lo = b_hi + GT_B_PLANE;
             const int kc = min(GT_KC, g.kext[sgi] - k0);
-            for (int kk = 0; kk < kc / 16; ++kk) {
-              const uint32_t a_off = (uint32_t)kk * 4096u, b_off = (uint32_t)kk * 2u * (uint32_t)N * 16u, b_lbo = (uint32_t)N * 16u;
-              mma_f16_ss(d_tmem, smem_desc(a_hi + a_off, 2048u, 128u), smem_desc(b_hi + b_off, b_lbo, 128u), idesc, accumulate);
-              accumulate = 1;
-              if (x3) {
-                mma_f16_ss(d_tmem, smem_desc(a_lo + a_off, 2048u, 128u), smem_desc(b_hi + b_off, b_lbo, 128u), idesc, 1);
-                mma_f16_ss(d_tmem, smem_desc(a_hi + a_off, 2048u, 128u), smem_desc(b_lo + b_off, b_lbo, 128u), idesc, 1);
+            if (elect_one()) {
+              uint32_t acc = accumulate;
+              for (int kk = 0; kk < kc / 16; ++kk) {
+                const uint32_t a_off = (uint32_t)kk * 4096u, b_off = (uint32_t)kk * 2u * (uint32_t)N * 16u, b_lbo = (uint32_t)N * 16u;
+                mma_f16_ss(d_tmem, smem_desc(a_hi + a_off, 2048u, 128u), smem_desc(b_hi + b_off, b_lbo, 128u), idesc, acc);
+                acc = 1;
+                if (x3) {
+                  mma_f16_ss(d_tmem, smem_desc(a_lo + a_off, 2048u, 128u), smem_desc(b_hi + b_off, b_lbo, 128u), idesc, 1);
+                  mma_f16_ss(d_tmem, smem_desc(a_hi + a_off, 2048u, 128u), smem_desc(b_lo + b_off, b_lbo, 128u), idesc, 1);
+                }
               }
+              mma_commit(empty(s));
             }
-            mma_commit(empty(s));
+            accumulate = 1;
           }
-        mma_commit(acc_full(b));
+        if (elect_one()) mma_commit(acc_full(b));
       }
     }
   } else {
@@ -694,6 +715,50 @@ __global__ void __launch_bounds__(128) colsum_packed_kernel(const uint4* __restr
 
 using namespace aon;
 
+// ---- tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency) ------------
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (TmapEncodeFn)p;
+  });
+  return fn;
+}
+// Encoded maps are pure functions of (pointer, shape, box): cached per thread ("lazily-created CUtensorMaps cached
+// per (ptr, shape)"), so a training step that re-uses its planes pays the ~1 us encode once.
+typedef std::tuple<const void*, int, int, int, int, int> TmapKey;
+static int tmap_get(const TmapKey& key, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+                    CUtensorMap* out) {
+  thread_local std::map<TmapKey, CUtensorMap> cache;
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return AON_OK; }
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return AON_E_UNSUPPORTED; }
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)rank, const_cast<void*>(std::get<0>(key)), dims, strides, box,
+                         ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return AON_E_CUDA; }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return AON_OK;
+}
+// PK(rows, feat) = [tiles][feat/8][128][8] x 16 bit, in 8-byte elements: box = GT_KC samples x `groups` feature groups of one tile
+static int tmap_packed(const void* base, int feat, int tiles, int groups, CUtensorMap* out) {
+  const cuuint64_t dims[3] = {256, (cuuint64_t)(feat / 8), (cuuint64_t)tiles};
+  const cuuint64_t strides[2] = {2048, (cuuint64_t)(feat / 8) * 2048};
+  const cuuint32_t box[3] = {GT_KC * 2, (cuuint32_t)groups, 1};
+  return tmap_get(TmapKey(base, 3, feat, tiles, groups, 0), 3, dims, strides, box, out);
+}
+
 extern "C" size_t aon_gemm_struct_size(void) { return sizeof(AonGemm); }
 
 extern "C" int aon_gemm_tc(const AonGemm* gp, aon_stream_t stream) {
@@ -730,7 +795,18 @@ extern "C" int aon_gemm_tc(const AonGemm* gp, aon_stream_t stream) {
     grid = dim3((unsigned)g.a_tiles, (unsigned)g.splits);
   }
   GtParams P;
+  memset(&P, 0, sizeof(P));
   P.g = g;
+  int rc;
+  if (g.mode == AON_GEMM_TN) {
+    AON_REQUIRE(g.a_off[0] + g.a_tiles * 128 <= g.a_feat[0] && g.b_off[0] + g.N <= g.b_feat[0], "aon_gemm_tc: TN operands out of range");
+    if ((rc = tmap_packed(g.a_hi[0], g.a_feat[0], g.m_tiles, 16, &P.tm[0])) != AON_OK) return rc;
+    if ((rc = tmap_packed(g.b_hi[0], g.b_feat[0], g.m_tiles, g.N / 8, &P.tm[2])) != AON_OK) return rc;
+    if (g.x3) {
+      if ((rc = tmap_packed(g.a_lo[0], g.a_feat[0], g.m_tiles, 16, &P.tm[1])) != AON_OK) return rc;
+      if ((rc = tmap_packed(g.b_lo[0], g.b_feat[0], g.m_tiles, g.N / 8, &P.tm[3])) != AON_OK) return rc;
+    }
+  }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (g.mode == AON_GEMM_NT && (g.N == 128 || g.N == 256) && g.m_tiles >= 2 * sms && !(g.reserved & 16)) {
