@@ -55,8 +55,12 @@ __device__ __forceinline__ void gt_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
 
+// fp16 operand planes carry power-of-two scaled values (activations x8, weights x64, gradients x2^k): a value beyond the
+// fp16 range would become inf and poison every accumulator it meets as NaN.  Saturate instead (finite, visibly clipped);
+// lit.Trainer checks the gradient buffer for non-finite values at its logging interval and raises.
+__device__ __forceinline__ float sat_h(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  return (uint32_t)__half_as_ushort(__float2half_rn(a)) | ((uint32_t)__half_as_ushort(__float2half_rn(b)) << 16);
+  return (uint32_t)__half_as_ushort(__float2half_rn(sat_h(a))) | ((uint32_t)__half_as_ushort(__float2half_rn(sat_h(b))) << 16);
 }
 
 __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(const __grid_constant__ GtParams P) {

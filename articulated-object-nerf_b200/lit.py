@@ -149,6 +149,64 @@ class FlatAdam(torch.optim.Optimizer):
         self.param_groups[0].update(sd["param_groups"][0])
 
 
+class GradSync:
+    """DDP-style gradient averaging that overlaps with the backward pass (run.py:109-111: PL's DDPPlugin buckets do the same).
+    The parameters' .grad are views of ONE flat buffer (FlatAdam); the buffer is cut into contiguous groups (fine MLP, coarse
+    MLP, code tables).  A post-accumulate hook counts the gradients of each group as autograd writes them; when a group is
+    complete its slice is all-reduced asynchronously (NCCL runs on its own stream), so the fine MLP's 2.4 MB travel while the
+    coarse MLP's backward is still computing.  ``finish()`` launches whatever is left, waits, and the optimizer applies the
+    1 / world factor (``grad_scale``) -- sums are all-reduced, the mean is taken in the Adam kernel."""
+
+    def __init__(self, named_params, flat_grad: Tensor, group_of=None):
+        import torch.distributed as dist
+        self.dist, self.flat = dist, flat_grad
+        self.world = D.world()[1]
+        self.groups, self.works = [], []
+        if self.world == 1:
+            return
+        group_of = group_of or (lambda name: name.split(".")[1] if name.startswith("model.") and name.count(".") > 1 else name.split(".")[0])
+        base, esz = flat_grad.data_ptr(), flat_grad.element_size()
+        by = {}
+        for name, p in named_params:
+            if not p.requires_grad or p.grad is None:
+                continue
+            off = (p.grad.data_ptr() - base) // esz
+            if not (0 <= off and off + p.numel() <= flat_grad.numel()):
+                raise L.AonError("GradSync: %s.grad is not a view of the flat gradient buffer" % name)
+            g = by.setdefault(group_of(name), {"lo": off, "hi": off + p.numel(), "n": 0, "seen": 0, "sent": False})
+            g["lo"], g["hi"], g["n"] = min(g["lo"], off), max(g["hi"], off + p.numel()), g["n"] + 1
+            p.register_post_accumulate_grad_hook(lambda _p, g=g: self._on_grad(g))
+        self.groups = sorted(by.values(), key=lambda g: g["lo"])
+        for a, b in zip(self.groups, self.groups[1:]):
+            if a["hi"] > b["lo"]:
+                raise L.AonError("GradSync: parameter groups are not contiguous in the flat buffer")
+
+    def _send(self, g):
+        g["sent"] = True
+        self.works.append(self.dist.all_reduce(self.flat[g["lo"]:g["hi"]], op=self.dist.ReduceOp.SUM, async_op=True))
+
+    def _on_grad(self, g):
+        g["seen"] += 1
+        if g["seen"] == g["n"] and not g["sent"]:
+            self._send(g)
+
+    def start(self):
+        for g in self.groups:
+            g["seen"], g["sent"] = 0, False
+        self.works = []
+
+    def finish(self) -> float:
+        """-> the factor the optimizer must apply to the summed gradients"""
+        if self.world == 1:
+            return 1.0
+        for g in self.groups:
+            if not g["sent"]:          # a group whose hooks did not all fire (a parameter without gradient this step)
+                self._send(g)
+        for w in self.works:
+            w.wait()
+        return 1.0 / self.world
+
+
 class _LitCommon(LitModel):
     near, far, white_bkgd = 2.0, 6.0, True     # datasets/sapien.py:72-73 constants; setup() may override
 
@@ -363,16 +421,25 @@ class Trainer:
                 torch.autograd.graph.increment_version(p)    # the packed-weight cache keys on parameter versions
         system._optimizer = opt                          # Adam moments survive repeated fit() calls
         system.train()
+        sync = getattr(system, "_grad_sync", None)
+        if sync is None:
+            sync = system._grad_sync = GradSync(list(system.named_parameters()), opt.flat_grad)
         for batch_idx, batch in enumerate(batches):
             if self.global_step >= self.max_steps:
                 break
             opt.zero_grad(set_to_none=False)
+            sync.start()
             loss = system.training_step(batch, batch_idx)
-            loss.backward()
-            if D.world()[1] > 1:
-                D.allreduce_mean_(opt.flat_grad)         # the gradients already live in one flat buffer
+            loss.backward()                              # the fine MLP's gradient slice is all-reduced while the coarse MLP's backward runs
+            opt.grad_scale = sync.finish()
             system.optimizer_step(0, batch_idx, opt, 0, None, False, False, False)
             self.global_step += 1
+            if self.log_every and self.global_step % self.log_every == 0:
+                # the fp16 hi+lo operand planes of the training GEMMs saturate instead of overflowing; a non-finite gradient
+                # (or loss) means the power-of-two operand scaling of train_tc.py does not fit this model / loss: fail loudly
+                if not bool(torch.isfinite(opt.flat_grad).all()) or not math.isfinite(system.logged.get("train/loss", 0.0)):
+                    raise L.AonError("non-finite training gradient / loss at step %d: operand range of the tcgen05 training GEMMs "
+                                     "exceeded (train_tc.py scales: activations x8, weights x64); use train_gemm = 'torch'" % self.global_step)
             if self.log_every and self.is_global_zero and self.global_step % self.log_every == 0:
                 print("step %d  %s" % (self.global_step, {k: round(v, 4) for k, v in system.logged.items()}), flush=True)
             if self.ckpt_every and self.on_checkpoint is not None and self.global_step % self.ckpt_every == 0:

@@ -93,6 +93,9 @@ class _VanillaMLPFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_raw):
+        if ctx.pk is None:
+            raise L.AonError("the tcgen05 training path frees its saved operand planes in backward(): a second backward through the "
+                             "same graph (retain_graph) is not supported -- re-run the forward, or set train_gemm = 'torch'")
         E, V, h, bott, hv = ctx.pk
         W = ctx.W
         M, tiles, S = ctx.dims
@@ -218,6 +221,9 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_raw):
+        if ctx.pk is None:
+            raise L.AonError("the tcgen05 training path frees its saved operand planes in backward(): a second backward through the "
+                             "same graph (retain_graph) is not supported -- re-run the forward, or set train_gemm = 'torch'")
         P, hd, warped, E, V, h, bott, hv = ctx.pk
         W, (s_, c_, a_), (M, tiles, S) = ctx.W, ctx.codes, ctx.dims
         dev = g_raw.device

@@ -391,12 +391,14 @@ def train_block(args, dev, world, rank, rays_o, rays_d):
     if args.kind != "vanilla":
         batch.update(instance_id=torch.tensor([0], device=dev), articulation_id=torch.tensor([3], device=dev))
 
+    sync = lit.GradSync(list(s.named_parameters()), opt.flat_grad)   # per-MLP slices all-reduced while the backward still runs
+
     def step(i):
         opt.zero_grad()
+        sync.start()
         loss = s.training_step(batch, i)
         loss.backward()
-        if world > 1:
-            D.allreduce_mean_(opt.flat_grad)
+        opt.grad_scale = sync.finish()
         s.optimizer_step(0, i, opt, 0, None, False, False, False)
         s.trainer.global_step += 1
 
@@ -418,7 +420,9 @@ def train_block(args, dev, world, rank, rays_o, rays_d):
     return {"value": world * Rb / (ms * 1e-3), "unit": "rays/s (training: forward + backward + all-reduce + Adam)", "ms_per_step": ms,
             "rays_per_gpu_per_step": Rb, "steps": K, "warmup": 3, "algorithmic_tflops_per_gpu": flop / (ms * 1e-3) / 1e12,
             "gemm": "tcgen05 kind::f16, fp16 hi+lo operands (3 MMAs per K step), fp32 accumulate" if s.model.train_gemm == "tc" else "library",
-            "aon_launches_per_step": L.launch_count() // K, "grad_allreduce_bytes": opt.flat_grad.numel() * 4 if world > 1 else 0}
+            "aon_launches_per_step": L.launch_count() // K, "grad_allreduce_bytes": opt.flat_grad.numel() * 4 if world > 1 else 0,
+            "grad_allreduce": "%d asynchronous all-reduces per step (fine MLP, coarse MLP%s), launched from post-accumulate hooks while the "
+                              "backward runs" % (len(sync.groups), ", code tables" if len(sync.groups) > 2 else "") if world > 1 else "none (1 rank)"}
 
 
 def sharded_block(scene, focal, c2w, world, rank, dev, flush, steps=5, warmup=2):

@@ -36,11 +36,64 @@ def _worker(rank, ws, port, q):
         # camera form (the fused image kernel generates its own rays: blocks are addressed by pixel range)
         goti = D.render_image_sharded(lambda lo, hi: full[lo:hi].clone(), R)
         ok &= goti.shape == full.shape and torch.equal(goti, full)
+    ok &= _grad_sync_case(rank, ws)
     g = torch.full((1000,), float(rank + 1))
     D.allreduce_mean_(g)
     ok &= torch.allclose(g, torch.full((1000,), (1 + ws) / 2.0 * 1.0))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
+
+
+def _grad_sync_case(rank, ws):
+    """lit.GradSync: per-module slices of a flat gradient buffer are all-reduced from post-accumulate hooks while the backward
+    runs; the result (times the returned factor) must equal the mean of the ranks' gradients."""
+    from aon_b200 import lit
+    torch.manual_seed(0)                                    # same weights on every rank
+
+    class Sys(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = torch.nn.Module()
+            self.model.coarse_mlp = torch.nn.Linear(5, 7)
+            self.model.fine_mlp = torch.nn.Linear(7, 3)
+            self.code_library = torch.nn.Embedding(4, 3)
+
+    s = Sys()
+    params = list(s.parameters())
+    flat = torch.zeros(sum(p.numel() for p in params))
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view(p.shape)
+        off += p.numel()
+    sync = lit.GradSync(list(s.named_parameters()), flat)
+    ok = len(sync.groups) == 3 and sync.groups[0]["lo"] == 0 and sync.groups[-1]["hi"] == flat.numel()
+    for step in range(2):
+        flat.zero_()
+        sync.start()
+        g = torch.Generator().manual_seed(100 * step + rank)  # different data per rank
+        x = torch.randn(9, 5, generator=g)
+        out = s.model.fine_mlp(torch.relu(s.model.coarse_mlp(x))) + (s.code_library(torch.tensor([rank % 4])) if step == 0 else 0)
+        out.square().mean().backward()
+        local = flat.clone() if False else None
+        scale = sync.finish()
+        got = flat * scale
+        # reference: every rank recomputes every rank's gradient
+        want = torch.zeros_like(flat)
+        for r in range(ws):
+            for p in params:
+                p.grad = None
+            g = torch.Generator().manual_seed(100 * step + r)
+            x = torch.randn(9, 5, generator=g)
+            out = s.model.fine_mlp(torch.relu(s.model.coarse_mlp(x))) + (s.code_library(torch.tensor([r % 4])) if step == 0 else 0)
+            out.square().mean().backward()
+            want += torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+        want /= ws
+        off = 0
+        for p in params:                                     # re-attach the flat views for the next step
+            p.grad = flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        ok &= bool(torch.allclose(got, want, atol=1e-6))
+    return ok
 
 
 def _free_port():

@@ -35,6 +35,9 @@ def test_psnr_protocol_short(built_lib):
     for name, p, dlt, cross in rows[1:]:
         assert abs(dlt) < 0.1, rows                                      # north_star: PSNR within 0.1 dB of the reference
     assert rows[1][3] > 80, rows                                         # f16x3 render ~identical to the reference render
+    # the articulated auto-decoder through the same protocol (stored views of known states + interpolated test-path frames)
+    rows = psnr_protocol.run(steps=120, wh=(32, 24), modes=("f16x3",), n_test=2, log=lambda *a: None, kind="autodecoder")
+    assert abs(rows[1][2]) < 0.1 and rows[1][3] > 60, rows
 
 
 def test_run_cli_train_then_eval(tmp_path, built_lib, monkeypatch):

@@ -37,6 +37,8 @@ def main():
     with open(out + ".md", "w") as f:
         f.write("# ncu --set full summary: %s (launch %d)\n\n" % (rep, idx))
         for k, v in d.items():
+            if "ops_path_tensor" in k and v["value"].strip() in ("0", "0.0"):
+                continue                 # the per-format tensor paths this kernel does not use
             f.write("- `%s` = %s %s\n" % (k, v["value"], v["unit"]))
         f.write("\ndram bytes per launch (read+write) = %.0f\n" % summary["dram_bytes_per_launch"])
     print(open(out + ".md").read())
