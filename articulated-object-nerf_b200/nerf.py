@@ -248,7 +248,8 @@ class _LevelLoop(nn.Module):
     def _init_cache(self):
         self._cache = {"coarse": _PackCache(), "fine": _PackCache()}
         self.precision = default_precision()
-        # training_step contractions: "tc" = hand-written tcgen05 GEMMs (train_tc.py; vanilla MLP), "torch" = library GEMMs
+        # training_step contractions: "tc" = hand-written tcgen05 GEMMs on fp16 hi+lo operand planes (train_tc.py; fp32-grade
+        # gradients), "tc16" = the same GEMMs on single fp16 planes (fast mode, ~1e-3 gradient noise), "torch" = library GEMMs
         self.train_gemm = os.environ.get("AON_TRAIN_GEMM", "tc")
 
     def _render(self, rays, randomized, white_bkgd, near, far, latents=None, t_rand=None, u=None):
@@ -294,12 +295,14 @@ class _LevelLoop(nn.Module):
                 t_vals = L.sample_pdf(t_vals, weights.detach().contiguous(), self.num_fine_samples,
                                       u=None if u is None else u.contiguous())
             samples = o[:, None, :] + t_vals[..., None] * d[:, None, :]
-            if latents is None and self.train_gemm == "tc":
-                raw_rgb, raw_sigma = train_tc.vanilla_mlp(pos_enc_cuda(samples, 0, 10), view_enc, samples.shape[1], mlp)
+            tc = self.train_gemm in ("tc", "tc16")           # tcgen05 GEMMs: fp16 hi+lo planes ("tc") or the hi plane only ("tc16")
+            if latents is None and tc:
+                raw_rgb, raw_sigma = train_tc.vanilla_mlp(pos_enc_cuda(samples, 0, 10), view_enc, samples.shape[1], mlp,
+                                                          x3=self.train_gemm == "tc")
             elif latents is None:
                 raw_rgb, raw_sigma = mlp(pos_enc_cuda(samples, 0, 10), view_enc)
-            elif self.train_gemm == "tc":
-                raw_rgb, raw_sigma = train_tc.autodecoder_mlp(samples.contiguous(), view_enc, latents, mlp)
+            elif tc:
+                raw_rgb, raw_sigma = train_tc.autodecoder_mlp(samples.contiguous(), view_enc, latents, mlp, x3=self.train_gemm == "tc")
             else:
                 raw_rgb, raw_sigma = mlp(samples, view_enc, latents)
             comp, acc, weights, depth = composite_cuda(raw_rgb, raw_sigma, t_vals, d, white_bkgd, 0 if latents is None else 1)

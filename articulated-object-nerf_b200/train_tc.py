@@ -21,6 +21,31 @@ from . import lib as L
 
 SA, SW = 8.0, 64.0
 
+# Operand planes: True = fp16 hi + lo (3 MMAs per K step; fp32-grade gradients, the default "tc" path); False = the hi plane
+# only (one MMA per K step, half the HBM traffic of every GEMM; ~1e-3 relative gradient noise -- the fast training mode
+# "tc16", to "tc" what the one-pass f16 eval mode is to f16x3).  Set per call by vanilla_mlp / autodecoder_mlp.
+_X3 = True
+
+
+def _PK(tiles, feat, dev):
+    return L.PK(tiles, feat, dev, _X3)
+
+
+def _pack_rows(*a, **k):
+    return L.pack_rows(*a, x3=_X3, **k)
+
+
+def _pack_linear(*a, **k):
+    return L.pack_linear(*a, x3=_X3, **k)
+
+
+def _gemm_nt(*a, **k):
+    return L.gemm_nt(*a, x3=_X3, **k)
+
+
+def _gemm_tn(*a, **k):
+    return L.gemm_tn(*a, x3=_X3, **k)
+
 
 def _pad(n: int, m: int) -> int:
     return (n + m - 1) // m * m
@@ -38,7 +63,7 @@ def _wgrad(dY: L.PK, out_valid: int, X: L.PK, x_off: int, n_cols: int, cols_vali
            inv: float) -> None:
     """dst[0:out_valid, col_off : col_off + cols_valid] = inv * dY^T X[:, x_off : x_off + n_cols]."""
     a_tiles = dY.feat // 128
-    part = L.gemm_tn(dY, 0, a_tiles, X, x_off, n_cols, max(1, 296 // a_tiles))
+    part = _gemm_tn(dY, 0, a_tiles, X, x_off, n_cols, max(1, 296 // a_tiles))
     L.wgrad_reduce(part, inv, dst, col_off, out_valid, cols_valid)
 
 
@@ -46,7 +71,7 @@ def _wgrad_head(X: L.PK, in_valid: int, G: L.PK, out_valid: int, dst: torch.Tens
     """Heads (1 / 3 output features, padded to 16): dst[o, i] = inv * sum_m G[m, o] X[m, i] as the transposed product
     (rows = the 128-feature tiles of X, columns = the 16 padded outputs)."""
     a_tiles = X.feat // 128
-    part = L.gemm_tn(X, 0, a_tiles, G, 0, 16, max(1, 296 // a_tiles))
+    part = _gemm_tn(X, 0, a_tiles, G, 0, 16, max(1, 296 // a_tiles))
     L.wgrad_reduce(part, inv, dst, 0, in_valid, out_valid, transpose=True)
 
 
@@ -56,36 +81,37 @@ class _VanillaMLPFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, view_enc, S, *params):
+        ctx.x3 = _X3
         M, dev = enc.shape[0], enc.device
         tiles = (M + 127) // 128
         W = [p.detach().contiguous() for p in params[0::2]]
         B = [p.detach() for p in params[1::2]]
-        E = L.pack_rows(enc.detach(), M, tiles, 64, SA)
-        V = L.pack_rows(view_enc.detach(), M, tiles, 32, SA, row_div=S)
+        E = _pack_rows(enc.detach(), M, tiles, 64, SA)
+        V = _pack_rows(view_enc.detach(), M, tiles, 32, SA, row_div=S)
         inv = 1.0 / (SA * SW)
         h: List[L.PK] = []
         x, kx = E, 64
         for i in range(8):
-            Wp = L.pack_linear(W[i], False, 256, _pad(W[i].shape[1], 16) if i != 5 else 320, SW)
+            Wp = _pack_linear(W[i], False, 256, _pad(W[i].shape[1], 16) if i != 5 else 320, SW)
             segs = [(x, 0, kx, Wp, 0, 0)]
             if i == 5:
                 segs.append((E, 0, 64, Wp, 256, 0))
-            out = L.PK(tiles, 256, dev)
-            L.gemm_nt(segs, 256, tiles, dev, bias=B[i].contiguous(), relu=True, inv_scale=inv, out=out, out_scale=SA)
+            out = _PK(tiles, 256, dev)
+            _gemm_nt(segs, 256, tiles, dev, bias=B[i].contiguous(), relu=True, inv_scale=inv, out=out, out_scale=SA)
             h.append(out)
             x, kx = out, 256
         raw = torch.empty(tiles * 128, 4, dtype=torch.float32, device=dev)
-        Wd = L.pack_linear(W[10], False, 16, 256, SW)
-        L.gemm_nt([(h[7], 0, 256, Wd, 0, 0)], 16, tiles, dev, bias=_pad_bias(B[10], 16), inv_scale=inv, out_f32=raw[:, 3:], n_valid=1)
-        Wb = L.pack_linear(W[9], False, 256, 256, SW)
-        bott = L.PK(tiles, 256, dev)
-        L.gemm_nt([(h[7], 0, 256, Wb, 0, 0)], 256, tiles, dev, bias=B[9].contiguous(), inv_scale=inv, out=bott, out_scale=SA)
-        Wv = L.pack_linear(W[8], False, 128, 288, SW)
-        hv = L.PK(tiles, 128, dev)
-        L.gemm_nt([(bott, 0, 256, Wv, 0, 0), (V, 0, 32, Wv, 256, 0)], 128, tiles, dev, bias=B[8].contiguous(), relu=True,
+        Wd = _pack_linear(W[10], False, 16, 256, SW)
+        _gemm_nt([(h[7], 0, 256, Wd, 0, 0)], 16, tiles, dev, bias=_pad_bias(B[10], 16), inv_scale=inv, out_f32=raw[:, 3:], n_valid=1)
+        Wb = _pack_linear(W[9], False, 256, 256, SW)
+        bott = _PK(tiles, 256, dev)
+        _gemm_nt([(h[7], 0, 256, Wb, 0, 0)], 256, tiles, dev, bias=B[9].contiguous(), inv_scale=inv, out=bott, out_scale=SA)
+        Wv = _pack_linear(W[8], False, 128, 288, SW)
+        hv = _PK(tiles, 128, dev)
+        _gemm_nt([(bott, 0, 256, Wv, 0, 0), (V, 0, 32, Wv, 256, 0)], 128, tiles, dev, bias=B[8].contiguous(), relu=True,
                   inv_scale=inv, out=hv, out_scale=SA)
-        Wr = L.pack_linear(W[11], False, 16, 128, SW)
-        L.gemm_nt([(hv, 0, 128, Wr, 0, 0)], 16, tiles, dev, bias=_pad_bias(B[11], 16), inv_scale=inv, out_f32=raw, n_valid=3)
+        Wr = _pack_linear(W[11], False, 16, 128, SW)
+        _gemm_nt([(hv, 0, 128, Wr, 0, 0)], 16, tiles, dev, bias=_pad_bias(B[11], 16), inv_scale=inv, out_f32=raw, n_valid=3)
         ctx.pk = (E, V, h, bott, hv)
         ctx.W = W
         ctx.dims = (M, tiles, S)
@@ -93,6 +119,8 @@ class _VanillaMLPFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_raw):
+        global _X3
+        _X3 = ctx.x3
         if ctx.pk is None:
             raise L.AonError("the tcgen05 training path frees its saved operand planes in backward(): a second backward through the "
                              "same graph (retain_graph) is not supported -- re-run the forward, or set train_gemm = 'torch'")
@@ -103,8 +131,8 @@ class _VanillaMLPFn(torch.autograd.Function):
         R = max(1, M // S)
         SG = float(2 ** int(math.floor(math.log2(R))))
         g_raw = g_raw.contiguous()
-        Gr = L.pack_rows(g_raw, M, tiles, 16, SG)                       # columns 0-2 (+ sigma in column 3, unused here: zero weight rows)
-        Gs = L.pack_rows(g_raw[:, 3:], M, tiles, 16, SG)                 # sigma gradient alone (C = 1)
+        Gr = _pack_rows(g_raw, M, tiles, 16, SG)                       # columns 0-2 (+ sigma in column 3, unused here: zero weight rows)
+        Gs = _pack_rows(g_raw[:, 3:], M, tiles, 16, SG)                 # sigma gradient alone (C = 1)
         inv_w = 1.0 / (SG * SA)
         gW = [torch.empty_like(w) for w in W]           # every entry is written by a wgrad_reduce launch
         gB = [None] * 12
@@ -113,24 +141,24 @@ class _VanillaMLPFn(torch.autograd.Function):
 
         # rgb_layer: the packed gradient has 4 live columns (r, g, b, sigma); W_r^T padded with zero rows ignores sigma
         _wgrad_head(hv, 128, Gr, 3, gW[11], inv_w)
-        WrT = L.pack_linear(W[11], True, 128, 16, SW)
-        d_hv = L.PK(tiles, 128, dev)
-        cs = L.gemm_nt([(Gr, 0, 16, WrT, 0, 0)], 128, tiles, dev, epi=L.EPI_MASK, mask=(hv, 0), inv_scale=1.0 / SW, out=d_hv, colsum=True)
+        WrT = _pack_linear(W[11], True, 128, 16, SW)
+        d_hv = _PK(tiles, 128, dev)
+        cs = _gemm_nt([(Gr, 0, 16, WrT, 0, 0)], 128, tiles, dev, epi=L.EPI_MASK, mask=(hv, 0), inv_scale=1.0 / SW, out=d_hv, colsum=True)
         # views_linear.0 : inputs [bottleneck(256), view enc(27)]
         _wgrad(d_hv, 128, bott, 0, 256, 256, gW[8], 0, inv_w)
         _wgrad(d_hv, 128, V, 0, 32, 27, gW[8], 256, inv_w)
         gB[8] = cs.sum(0) / SG
-        WvT = L.pack_linear(W[8], True, 288, 128, SW)
-        d_bott = L.PK(tiles, 256, dev)
-        cs = L.gemm_nt([(d_hv, 0, 128, WvT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / SW, out=d_bott, colsum=True)
+        WvT = _pack_linear(W[8], True, 288, 128, SW)
+        d_bott = _PK(tiles, 256, dev)
+        cs = _gemm_nt([(d_hv, 0, 128, WvT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / SW, out=d_bott, colsum=True)
         # bottleneck_layer and density_layer both read the last trunk activation h[7]
         _wgrad(d_bott, 256, h[7], 0, 256, 256, gW[9], 0, inv_w)
         gB[9] = cs.sum(0) / SG
         _wgrad_head(h[7], 256, Gs, 1, gW[10], inv_w)
-        WbT = L.pack_linear(W[9], True, 256, 256, SW)
-        WdT = L.pack_linear(W[10], True, 256, 16, SW)
-        d = L.PK(tiles, 256, dev)
-        cs = L.gemm_nt([(d_bott, 0, 256, WbT, 0, 0), (Gs, 0, 16, WdT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[7], 0),
+        WbT = _pack_linear(W[9], True, 256, 256, SW)
+        WdT = _pack_linear(W[10], True, 256, 16, SW)
+        d = _PK(tiles, 256, dev)
+        cs = _gemm_nt([(d_bott, 0, 256, WbT, 0, 0), (Gs, 0, 16, WdT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[7], 0),
                        inv_scale=1.0 / SW, out=d, colsum=True)
         # trunk, last layer first: pts_linears.i maps x_i -> h[i], x_0 = E, x_i = h[i-1] (+ E for i = 5)
         for i in range(7, -1, -1):
@@ -142,9 +170,9 @@ class _VanillaMLPFn(torch.autograd.Function):
             gB[i] = cs.sum(0) / SG                           # column sums of d, produced by the GEMM that wrote d
             if i == 0:
                 break
-            WT = L.pack_linear(W[i], True, 320 if i == 5 else 256, 256, SW)
-            nd = L.PK(tiles, 256, dev)
-            cs = L.gemm_nt([(d, 0, 256, WT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[i - 1], 0), inv_scale=1.0 / SW, out=nd,
+            WT = _pack_linear(W[i], True, 320 if i == 5 else 256, 256, SW)
+            nd = _PK(tiles, 256, dev)
+            cs = _gemm_nt([(d, 0, 256, WT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[i - 1], 0), inv_scale=1.0 / SW, out=nd,
                            colsum=True)
             d = nd
         ctx.pk = None
@@ -170,6 +198,7 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pos, view_enc, S, shape, app, art, *params):
+        ctx.x3 = _X3
         M, dev = pos.shape[0], pos.device
         tiles = (M + 127) // 128
         W = [p.detach().contiguous() for p in params[0::2]]
@@ -179,27 +208,27 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
         pos = pos.detach().contiguous()
 
         def lin(segs, w, k_pad, n, bias, relu):
-            Wp = L.pack_linear(w, False, n, k_pad, SW)
-            out = L.PK(tiles, n, dev)
-            L.gemm_nt([(x, 0, k, Wp, off, 0) for x, k, off in segs], n, tiles, dev, bias=bias, relu=relu, inv_scale=inv, out=out,
+            Wp = _pack_linear(w, False, n, k_pad, SW)
+            out = _PK(tiles, n, dev)
+            _gemm_nt([(x, 0, k, Wp, off, 0) for x, k, off in segs], n, tiles, dev, bias=bias, relu=relu, inv_scale=inv, out=out,
                       out_scale=SA)
             return out
 
         def head(x, k, w, bias, n_valid):
-            Wp = L.pack_linear(w, False, 16, k, SW)
+            Wp = _pack_linear(w, False, 16, k, SW)
             o = torch.empty(tiles * 128, n_valid, dtype=torch.float32, device=dev)
-            L.gemm_nt([(x, 0, k, Wp, 0, 0)], 16, tiles, dev, bias=_pad_bias(bias, 16), inv_scale=inv, out_f32=o, n_valid=n_valid)
+            _gemm_nt([(x, 0, k, Wp, 0, 0)], 16, tiles, dev, bias=_pad_bias(bias, 16), inv_scale=inv, out_f32=o, n_valid=n_valid)
             return o
 
         # articulation warp: deformation MLP on [pos, shape, articulation]
-        P = L.pack_rows(pos, M, tiles, 16, SA)
+        P = _pack_rows(pos, M, tiles, 16, SA)
         hd = [lin([(P, 16, 0)], W[0], 176, 128, _fold(B[0], W[0], [(3, s_), (131, a_)]), True)]
         for i in (1, 2, 3):
             hd.append(lin([(hd[-1], 128, 0)], W[i], 128, 128, B[i].contiguous(), True))
         delta = head(hd[3], 128, W[4], B[4], 3)
         warped = (delta[:M] + pos).contiguous()                                     # model_autodecoder.py:203
-        E = L.pack_rows(L.pos_enc(warped, 10), M, tiles, 64, SA)
-        V = L.pack_rows(view_enc.detach(), M, tiles, 32, SA, row_div=S)
+        E = _pack_rows(L.pos_enc(warped, 10), M, tiles, 64, SA)
+        V = _pack_rows(view_enc.detach(), M, tiles, 32, SA, row_div=S)
         h = [lin([(E, 64, 0)], W[5], 192, 256, _fold(B[5], W[5], [(63, s_)]), True)]
         for i in range(1, 8):
             if i == 5:
@@ -207,20 +236,22 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
             else:
                 h.append(lin([(h[-1], 256, 0)], W[5 + i], 256, 256, B[5 + i].contiguous(), True))
         raw = torch.empty(tiles * 128, 4, dtype=torch.float32, device=dev)
-        Wd = L.pack_linear(W[18], False, 16, 256, SW)
-        L.gemm_nt([(h[7], 0, 256, Wd, 0, 0)], 16, tiles, dev, bias=_pad_bias(B[18], 16), inv_scale=inv, out_f32=raw[:, 3:], n_valid=1)
+        Wd = _pack_linear(W[18], False, 16, 256, SW)
+        _gemm_nt([(h[7], 0, 256, Wd, 0, 0)], 16, tiles, dev, bias=_pad_bias(B[18], 16), inv_scale=inv, out_f32=raw[:, 3:], n_valid=1)
         bott = lin([(h[7], 256, 0)], W[17], 256, 256, B[17].contiguous(), False)
         hv = [lin([(bott, 256, 0), (V, 32, 256)], W[13], 416, 128, _fold(B[13], W[13], [(283, c_)]), True)]
         for i in (1, 2, 3):
             hv.append(lin([(hv[-1], 128, 0)], W[13 + i], 128, 128, B[13 + i].contiguous(), True))
-        Wr = L.pack_linear(W[19], False, 16, 128, SW)
-        L.gemm_nt([(hv[3], 0, 128, Wr, 0, 0)], 16, tiles, dev, bias=_pad_bias(B[19], 16), inv_scale=inv, out_f32=raw, n_valid=3)
+        Wr = _pack_linear(W[19], False, 16, 128, SW)
+        _gemm_nt([(hv[3], 0, 128, Wr, 0, 0)], 16, tiles, dev, bias=_pad_bias(B[19], 16), inv_scale=inv, out_f32=raw, n_valid=3)
         ctx.pk = (P, hd, warped, E, V, h, bott, hv)
         ctx.W, ctx.codes, ctx.dims = W, (s_, c_, a_), (M, tiles, S)
         return raw[:M]
 
     @staticmethod
     def backward(ctx, g_raw):
+        global _X3
+        _X3 = ctx.x3
         if ctx.pk is None:
             raise L.AonError("the tcgen05 training path frees its saved operand planes in backward(): a second backward through the "
                              "same graph (retain_graph) is not supported -- re-run the forward, or set train_gemm = 'torch'")
@@ -236,9 +267,9 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
 
         def dgrad(segs, n, mask, rows_pad, k_pad):
             """segs: [(dY, kext, weight index, first row of W^T)] -> (PK(tiles, n) masked by `mask`, its column sums / SG)."""
-            out = L.PK(tiles, n, dev)
-            gs = [(dY, 0, k, L.pack_linear(W[wi], True, rows_pad[j], k_pad[j], SW), 0, r0) for j, (dY, k, wi, r0) in enumerate(segs)]
-            cs = L.gemm_nt(gs, n, tiles, dev, epi=L.EPI_MASK, mask=None if mask is None else (mask, 0), inv_scale=1.0 / SW, out=out,
+            out = _PK(tiles, n, dev)
+            gs = [(dY, 0, k, _pack_linear(W[wi], True, rows_pad[j], k_pad[j], SW), 0, r0) for j, (dY, k, wi, r0) in enumerate(segs)]
+            cs = _gemm_nt(gs, n, tiles, dev, epi=L.EPI_MASK, mask=None if mask is None else (mask, 0), inv_scale=1.0 / SW, out=out,
                            colsum=True)
             return out, cs.sum(0) / SG
 
@@ -250,8 +281,8 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
                 acc += W[wi][:, c0:c0 + n].t() @ gb
 
         # ---- colour branch ----
-        Gr = L.pack_rows(g_raw, M, tiles, 16, SG)
-        Gs = L.pack_rows(g_raw[:, 3:], M, tiles, 16, SG)
+        Gr = _pack_rows(g_raw, M, tiles, 16, SG)
+        Gs = _pack_rows(g_raw[:, 3:], M, tiles, 16, SG)
         gB[19], gB[18] = g_raw[:, :3].sum(0), g_raw[:, 3:].sum(0)
         _wgrad_head(hv[3], 128, Gr, 3, gW[19], inv_w)
         d, cs = dgrad([(Gr, 16, 19, 0)], 128, hv[3], [128], [16])
@@ -285,11 +316,11 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
             d, cs = dgrad([(d, 256, wi, 0)], 256, h[i - 1], [448 if i == 5 else 256], [256])
         # ---- encoding -> warped position -> deformation MLP ----
         g_enc = torch.empty(tiles * 128, 63, dtype=torch.float32, device=dev)
-        W0T, W5T = L.pack_linear(W[5], True, 192, 256, SW), L.pack_linear(W[10], True, 448, 256, SW)
-        L.gemm_nt([(d, 0, 256, W0T, 0, 0), (d5, 0, 256, W5T, 0, 256)], 64, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / (SW * SG),
+        W0T, W5T = _pack_linear(W[5], True, 192, 256, SW), _pack_linear(W[10], True, 448, 256, SW)
+        _gemm_nt([(d, 0, 256, W0T, 0, 0), (d5, 0, 256, W5T, 0, 256)], 64, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / (SW * SG),
                   out_f32=g_enc, n_valid=63)
         g_warped = L.pos_enc_backward(warped, g_enc[:M], 10)                        # [M,3]; d warped / d delta = 1
-        Gd = L.pack_rows(g_warped, M, tiles, 16, SG)
+        Gd = _pack_rows(g_warped, M, tiles, 16, SG)
         gB[4] = g_warped.sum(0)
         _wgrad_head(hd[3], 128, Gd, 3, gW[4], inv_w)
         d, cs = dgrad([(Gd, 16, 4, 0)], 128, hd[3], [128], [16])
@@ -307,9 +338,12 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
         return tuple(out)
 
 
-def autodecoder_mlp(pos: torch.Tensor, view_enc: torch.Tensor, latents: dict, mlp) -> tuple:
+def autodecoder_mlp(pos: torch.Tensor, view_enc: torch.Tensor, latents: dict, mlp, x3: bool = True) -> tuple:
     """pos [R,S,3] raw sample positions, view_enc [R,27], latents {density, color, articulation} -> (raw_rgb [R,S,3],
-    raw_sigma [R,S,1]) through the tcgen05 GEMMs; gradients flow to the parameters and the three codes."""
+    raw_sigma [R,S,1]) through the tcgen05 GEMMs; gradients flow to the parameters and the three codes.
+    x3 = False: single fp16 operand planes (fast training mode)."""
+    global _X3
+    _X3 = bool(x3)
     R, S, _ = pos.shape
     params = []
     for lin in mlp.linears():
@@ -319,8 +353,11 @@ def autodecoder_mlp(pos: torch.Tensor, view_enc: torch.Tensor, latents: dict, ml
     return raw[:, :3].reshape(R, S, 3), raw[:, 3:].reshape(R, S, 1)
 
 
-def vanilla_mlp(enc: torch.Tensor, view_enc: torch.Tensor, S: int, mlp) -> tuple:
-    """enc [R,S,63] / [M,63], view_enc [R,27] -> (raw_rgb [R,S,3], raw_sigma [R,S,1]) through the tcgen05 GEMMs."""
+def vanilla_mlp(enc: torch.Tensor, view_enc: torch.Tensor, S: int, mlp, x3: bool = True) -> tuple:
+    """enc [R,S,63] / [M,63], view_enc [R,27] -> (raw_rgb [R,S,3], raw_sigma [R,S,1]) through the tcgen05 GEMMs.
+    x3 = False: single fp16 operand planes (fast training mode)."""
+    global _X3
+    _X3 = bool(x3)
     params = []
     for lin in mlp.linears():
         params += [lin.weight, lin.bias]

@@ -22,7 +22,8 @@ SURVEY.md 8a) of one synthetic SAPIEN-shaped 640x480 view (307 200 rays) per GPU
 * c2        BASELINE configs[2]: auto-decoder (2-part articulated model) at 320x240 and 640x480 on one GPU
 * c4        BASELINE configs[4]: auto-decoder, 4 articulation states (ids 0, 6, 12, 18 of the 19-row test table) x one
             640x480 view each, every image sharded over the N ranks
-* train     BASELINE configs[3]: training step (forward + backward + gradient all-reduce + Adam), 2048 rays per GPU
+* train     BASELINE configs[3]: training step (forward + backward + gradient all-reduce + Adam), 2048 rays per GPU;
+            train_fast = the same step on single fp16 operand planes (not the fp32-grade default)
 * fast_mode the single-pass fp16 mode of the same kernel (PSNR-level agreement, not the 1e-4 parity mode)
 
 --impl reference times the reference's own CPU implementation (same modules as cpu_baseline) with all host threads.
@@ -367,7 +368,7 @@ def max_over_ranks(ms, world, dev):
     return t.item()
 
 
-def train_block(args, dev, world, rank, rays_o, rays_d):
+def train_block(args, dev, world, rank, rays_o, rays_d, gemm="tc"):
     """training_step + backward + gradient all-reduce + optimizer_step of the Lightning-surface module at the reference's
     per-GPU batch (2048 rays vanilla, model.py:426; 4096 rays sapien_multi, sapien_multi.py:235), randomized sampling,
     3 warm-up + 10 timed steps, CUDA events, max over ranks.  MLP contractions: tcgen05 GEMMs (train_tc.py)."""
@@ -382,6 +383,7 @@ def train_block(args, dev, world, rank, rays_o, rays_d):
     Rb = 2048 if args.kind == "vanilla" else 4096
     s = lit.build_system(SimpleNamespace(exp_type=exp, run_max_steps=100000, white_back=True, N_max_objs=1, N_obj_code_length=128)).to(dev)
     s.train()
+    s.model.train_gemm = gemm
     s.trainer = SimpleNamespace(global_step=0, is_global_zero=rank == 0)
     opt = s.configure_optimizers()
     torch.manual_seed(1234 + rank)                # ... and a different ray batch / different sampling draws per rank
@@ -419,7 +421,8 @@ def train_block(args, dev, world, rank, rays_o, rays_d):
     flop = 3 * Rb * (S0 + S1) * FLOP_PER_SAMPLE[args.kind]
     return {"value": world * Rb / (ms * 1e-3), "unit": "rays/s (training: forward + backward + all-reduce + Adam)", "ms_per_step": ms,
             "rays_per_gpu_per_step": Rb, "steps": K, "warmup": 3, "algorithmic_tflops_per_gpu": flop / (ms * 1e-3) / 1e12,
-            "gemm": "tcgen05 kind::f16, fp16 hi+lo operands (3 MMAs per K step), fp32 accumulate" if s.model.train_gemm == "tc" else "library",
+            "gemm": {"tc": "tcgen05 kind::f16, fp16 hi+lo operands (3 MMAs per K step), fp32 accumulate",
+                     "tc16": "tcgen05 kind::f16, single fp16 operand planes (1 MMA per K step; fast training mode, ~1e-3 gradient noise), fp32 accumulate"}.get(s.model.train_gemm, "library"),
             "aon_launches_per_step": L.launch_count() // K, "grad_allreduce_bytes": opt.flat_grad.numel() * 4 if world > 1 else 0,
             "grad_allreduce": "%d asynchronous all-reduces per step (fine MLP, coarse MLP%s), launched from post-accumulate hooks while the "
                               "backward runs" % (len(sync.groups), ", code tables" if len(sync.groups) > 2 else "") if world > 1 else "none (1 rank)"}
@@ -703,8 +706,11 @@ def main():
         if world == 1 and args.kind == "vanilla":
             c2 = guarded("c2", c2_block, prec, prec_name, dev, flush, peak)
         c4 = guarded("c4", c4_block, prec, prec_name, world, rank, dev, flush)
+    train_fast = None
     if not args.no_train:
         train = guarded("train", train_block, args, dev, world, rank, rays_o, rays_d)
+        if not args.no_extras:
+            train_fast = guarded("train_fast", train_block, args, dev, world, rank, rays_o, rays_d, "tc16")
 
     if rank == 0:
         flop_k = FLOP_PER_SAMPLE[args.kind] * (S0 + S1) * R_k
@@ -734,7 +740,7 @@ def main():
                          "step_share": {"fused_kernel_ms_scaled_to_full_image": kern_ms * R / R_k, "step_ms": ms_total / args.steps}},
             "clocks": clk.report(),
         }
-        for k, v in (("fast_mode", fast), ("sharded", sharded), ("c2", c2), ("c4", c4), ("train", train)):
+        for k, v in (("fast_mode", fast), ("sharded", sharded), ("c2", c2), ("c4", c4), ("train", train), ("train_fast", train_fast)):
             if v is not None:
                 line[k] = v
         if not args.no_cpu_baseline and world == 1:

@@ -18,10 +18,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=20)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
-for exp, R in (("vanilla", 2048), ("vanilla_autodecoder", 4096)):
+for exp, R, gemm in (("vanilla", 2048, "tc"), ("vanilla_autodecoder", 4096, "tc"), ("vanilla", 2048, "tc16"), ("vanilla_autodecoder", 4096, "tc16")):
     torch.manual_seed(0)
     s = lit.build_system(SimpleNamespace(exp_type=exp, run_max_steps=1000, white_back=True, N_max_objs=1, N_obj_code_length=128)).to(dev)
     s.train()
+    s.model.train_gemm = gemm            # "tc": fp16 hi+lo operand planes (fp32-grade); "tc16": single fp16 planes (fast mode)
     o, d = L.raygen(480, 640, synth.sapien_focal(480), synth.sapien_camera(0), dev)
     idx = torch.randperm(o.shape[0], device=dev)[:R]
     batch = {"rays_o": o[idx][None], "rays_d": d[idx][None], "viewdirs": d[idx][None], "target": torch.rand(1, R, 3, device=dev)}
@@ -50,5 +51,5 @@ for exp, R in (("vanilla", 2048), ("vanilla_autodecoder", 4096)):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     flop = 3 * R * 258 * (1186816 if exp == "vanilla" else 1589760)
-    print("%-20s %5d rays/step: %.2f ms/step -> %.0f rays/s training, %.1f algorithmic TFLOP/s (fwd+bwd = 3x fwd), "
-          "%d aon kernel launches/step, loss %.4f" % (exp, R, ms, R / ms * 1e3, flop / ms * 1e-9, L.launch_count() // args.steps, loss.item()))
+    print("%-20s %-4s %5d rays/step: %.2f ms/step -> %.0f rays/s training, %.1f algorithmic TFLOP/s (fwd+bwd = 3x fwd), "
+          "%d aon kernel launches/step, loss %.4f" % (exp, gemm, R, ms, R / ms * 1e3, flop / ms * 1e-9, L.launch_count() // args.steps, loss.item()))
