@@ -515,10 +515,13 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo32) {
 }
 
 // named barrier shared by the two epilogue warps of a TMEM lane quadrant (ids 1..4)
-__device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void pair_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+// (bar.sync / bar.arrive are warp-aligned instructions: __syncwarp() first, so that lanes that took different branches just
+// before -- e.g. the padding rays of a ragged tile -- are converged again when the warp reaches the barrier)
+__device__ __forceinline__ void pair_bar_sync(int id) { __syncwarp(); asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_bar_arrive(int id) { __syncwarp(); asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 // named barrier of the epilogue + encoder warps (0-11) around the in-kernel hierarchical sampling of the fused kernel
-__device__ __forceinline__ void level_bar_sync() { asm volatile("bar.sync 5, 384;" ::: "memory"); }
+// (not inlined: the epilogue and the encoder warps then wait at the SAME barrier instruction, which is what synccheck expects)
+__device__ __noinline__ void level_bar_sync() { __syncwarp(); asm volatile("bar.sync 5, 384;" ::: "memory"); }
 
 // ray `row` of this CTA's tile: origin, direction, view direction (clamped to the last ray for the padding rows)
 __device__ __forceinline__ void load_ray(const TcParams& p, int row, float (&o)[3], float (&d)[3], float (&v)[3]) {
@@ -935,6 +938,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           if (tid < 4) s_par[off + n + tid] = b[tid];
           off += n + 4;
         }
+        __syncwarp();
         asm volatile("bar.sync 6, 256;" ::: "memory");
       }
       const float* tv = level == 0 ? p.t_vals + (p.t_stride ? rl * p.t_stride : 0) : slot_t1 + row * S1L;

@@ -225,6 +225,23 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// same update with the seven step-dependent scalars read from DEVICE memory: a captured CUDA graph of the training step bakes
+// kernel arguments in, so the learning-rate schedule and the bias corrections have to arrive through a buffer that the host
+// refreshes (one 28-byte copy) before every replay
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long n, const float* __restrict__ sc) {
+  const float omb1 = sc[0], beta2 = sc[1], omb2 = sc[2], eps = sc[3], step_size = sc[4], sqrt_bc2 = sc[5], grad_scale = sc[6];
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = fmaf(gi - m[i], omb1, m[i]);
+    const float vi = fmaf(gi * gi, omb2, v[i] * beta2);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrt_bc2 + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+
 static inline int grid_for(long n, int block) {
   long g = (n + block - 1) / block;
   const long cap = 148L * 16;
@@ -294,6 +311,23 @@ extern "C" int aon_adam_step(float* params, const float* grads, float* exp_avg, 
   adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2,
                                                                   (float)(1.0 - beta2), (float)eps, (float)(lr / bc1),
                                                                   (float)sqrt(bc2), (float)grad_scale);
+  AON_LAUNCH_CHECK();
+  return AON_OK;
+}
+
+extern "C" int aon_adam_scalars(double lr, double beta1, double beta2, double eps, long step, double grad_scale, float* out7_host) {
+  AON_REQUIRE(out7_host && step >= 1, "aon_adam_scalars: bad argument");
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  out7_host[0] = (float)(1.0 - beta1); out7_host[1] = (float)beta2; out7_host[2] = (float)(1.0 - beta2); out7_host[3] = (float)eps;
+  out7_host[4] = (float)(lr / bc1); out7_host[5] = (float)sqrt(bc2); out7_host[6] = (float)grad_scale;
+  return AON_OK;
+}
+
+extern "C" int aon_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, const float* scalars7_dev,
+                                 aon_stream_t stream) {
+  AON_REQUIRE(params && grads && exp_avg && exp_avg_sq && scalars7_dev && n >= 0, "aon_adam_step_dev: bad argument");
+  if (n == 0) return AON_OK;
+  adam_dev_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, scalars7_dev);
   AON_LAUNCH_CHECK();
   return AON_OK;
 }

@@ -44,6 +44,8 @@ SYMBOLS = {
     "aon_composite": (_i, [_fp, _fp, _fp, _l, _fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _vp]),
     "aon_composite_backward": (_i, [_fp, _fp, _fp, _l, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),
     "aon_adam_step": (_i, [_fp, _fp, _fp, _fp, _l, _d, _d, _d, _d, _l, _d, _vp]),
+    "aon_adam_scalars": (_i, [_d, _d, _d, _d, _l, _d, C.POINTER(_f)]),
+    "aon_adam_step_dev": (_i, [_fp, _fp, _fp, _fp, _l, _fp, _vp]),
     "aon_gemm_tc": (_i, [_vp, _vp]),
     "aon_gemm_struct_size": (_sz, []),
     "aon_pack_rows": (_i, [_fp, _l, _i, _l, _i, _i, _i, _f, _vp, _vp, _vp]),
@@ -95,6 +97,27 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _Null()
+
+
+def _on(device):
+    """`with torch.cuda.device(d)` costs ~10 us of host time per call -- more than enqueueing the kernel -- and a training step
+    makes ~300 calls: switch only when the tensor's device is not already the current one."""
+    d = torch.device(device) if not isinstance(device, torch.device) else device
+    idx = d.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(d)
+
+
 def launch_count(reset: bool = False) -> int:
     return int(load().aon_launch_count(1 if reset else 0))
 
@@ -130,7 +153,7 @@ def pack_weights(kind: int, precision: int, weights: Sequence[torch.Tensor], bia
         out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     wp = (C.c_void_p * n)(*[_ptr(w, "weight") for w, _ in keep])
     bp = (C.c_void_p * n)(*[_ptr(b, "bias") for _, b in keep])
-    with torch.cuda.device(dev):
+    with _on(dev):
         _check(lib.aon_pack_weights(kind, precision, wp, bp, out.data_ptr(), out.numel(), _stream()), "aon_pack_weights")
     return out
 
@@ -139,7 +162,7 @@ def fold_latents(kind: int, precision: int, packed: torch.Tensor, shape: torch.T
                  articulation: torch.Tensor) -> torch.Tensor:
     lib = load()
     folded = torch.empty(lib.aon_folded_floats(kind), dtype=torch.float32, device=packed.device)
-    with torch.cuda.device(packed.device):
+    with _on(packed.device):
         _check(lib.aon_fold_latents(kind, precision, packed.data_ptr(), _ptr(shape.reshape(-1), "shape"),
                                     _ptr(appearance.reshape(-1), "appearance"),
                                     _ptr(articulation.reshape(-1), "articulation"), _ptr(folded), _stream()),
@@ -154,7 +177,7 @@ def raygen(H: int, W: int, focal: float, c2w, device) -> tuple:
     arr = (C.c_float * 12)(*c.tolist())
     o = torch.empty(H * W, 3, dtype=torch.float32, device=device)
     d = torch.empty(H * W, 3, dtype=torch.float32, device=device)
-    with torch.cuda.device(o.device):
+    with _on(o.device):
         _check(lib.aon_raygen(H, W, float(focal), arr, _ptr(o), _ptr(d), _stream()), "aon_raygen")
     return o, d
 
@@ -164,7 +187,7 @@ def sample_along_rays(near: float, far: float, n_points: int, R: int, device, t_
     lib = load()
     shape = (n_points,) if t_rand is None else (R, n_points)
     t = torch.empty(shape, dtype=torch.float32, device=device)
-    with torch.cuda.device(t.device):
+    with _on(t.device):
         _check(lib.aon_sample_along_rays(float(near), float(far), n_points, _ptr(t_rand, "t_rand"), R, _ptr(t), _stream()),
                "aon_sample_along_rays")
     return t
@@ -221,7 +244,7 @@ def render_level(kind: int, precision: int, packed: torch.Tensor, folded: Option
     acc = torch.empty(R, dtype=torch.float32, device=dev)
     depth = torch.empty(R, dtype=torch.float32, device=dev)
     w = torch.empty(R, S, dtype=torch.float32, device=dev) if want_weights else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = workspace(dev, precision, R)
         _check(lib.aon_render_level(kind, precision, packed.data_ptr(), _ptr(folded, "folded"), _ptr(rays_o, "rays_o"),
                                     _ptr(rays_d, "rays_d"), _ptr(viewdirs, "viewdirs"), _ptr(t_vals, "t_vals"), stride,
@@ -238,7 +261,7 @@ def sample_pdf(t_coarse: torch.Tensor, weights: torch.Tensor, n_fine: int, u: Op
     t_stride = 0 if t_coarse.dim() == 1 else nc
     u_stride = 0 if (u is None or u.dim() == 1) else n_fine
     out = torch.empty(R, nc + n_fine, dtype=torch.float32, device=weights.device)
-    with torch.cuda.device(weights.device):
+    with _on(weights.device):
         _check(lib.aon_sample_pdf(_ptr(t_coarse, "t_coarse"), t_stride, _ptr(weights, "weights"), _ptr(u, "u"), u_stride,
                                   R, nc, n_fine, _ptr(out), _stream()), "aon_sample_pdf")
     return out
@@ -258,7 +281,7 @@ def render_rays(kind: int, precision: int, packed_coarse, packed_fine, folded_co
         raise AonError("render_rays: t_coarse must be [R,65]")
     if u is not None and tuple(u.shape) != (R, 128):
         raise AonError("render_rays: u must be [R,128]")
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = workspace(dev, precision, R)
         _check(lib.aon_render_rays(kind, precision, packed_coarse.data_ptr(), packed_fine.data_ptr(), _ptr(folded_coarse, "folded"),
                                    _ptr(folded_fine, "folded"), _ptr(rays_o, "rays_o"), _ptr(rays_d, "rays_d"),
@@ -282,7 +305,7 @@ def render_image(kind: int, precision: int, packed_coarse, packed_fine, folded_c
     if out is None:
         out = torch.empty(R, 5, dtype=torch.float32, device=dev)
     cout = torch.empty(R, 5, dtype=torch.float32, device=dev) if want_coarse else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = workspace(dev, precision, R)
         _check(lib.aon_render_image(kind, precision, packed_coarse.data_ptr(), packed_fine.data_ptr(), _ptr(folded_coarse, "folded"),
                                     _ptr(folded_fine, "folded"), arr, float(focal), H, W, int(ray0), R, float(near), float(far),
@@ -303,7 +326,7 @@ def render_image_host(kind: int, precision: int, packed_coarse, packed_fine, fol
     if out is None:
         out = torch.empty(R, 5, dtype=torch.float32).pin_memory()
     dev = packed_coarse.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = workspace(dev, precision, R)
         _check(lib.aon_render_image_host(kind, precision, packed_coarse.data_ptr(), packed_fine.data_ptr(),
                                          _ptr(folded_coarse, "folded"), _ptr(folded_fine, "folded"),
@@ -321,7 +344,7 @@ def pos_enc(x: torch.Tensor, max_deg: int) -> torch.Tensor:
     lib = load()
     n = x.numel() // 3
     out = torch.empty(tuple(x.shape[:-1]) + (3 + 6 * max_deg,), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _check(lib.aon_pos_enc(_ptr(x, "x"), n, max_deg, _ptr(out), _stream()), "aon_pos_enc")
     return out
 
@@ -329,7 +352,7 @@ def pos_enc(x: torch.Tensor, max_deg: int) -> torch.Tensor:
 def pos_enc_backward(x: torch.Tensor, g_out: torch.Tensor, max_deg: int) -> torch.Tensor:
     lib = load()
     gx = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _check(lib.aon_pos_enc_backward(_ptr(x, "x"), _ptr(g_out, "g_out"), x.numel() // 3, max_deg, _ptr(gx), _stream()),
                "aon_pos_enc_backward")
     return gx
@@ -345,7 +368,7 @@ def composite(raw_rgb: torch.Tensor, raw_sigma: torch.Tensor, t_vals: torch.Tens
     stride = 0 if t_vals.dim() == 1 else S
     e = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
     rgb, acc, depth, w, tr = e(R, 3), e(R), e(R), e(R, S), e(R, S)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _check(lib.aon_composite(_ptr(raw_rgb, "raw_rgb"), _ptr(raw_sigma, "raw_sigma"), _ptr(t_vals, "t_vals"), stride,
                                  _ptr(dirs, "dirs"), R, S, int(bool(white_bkgd)), act_mode, _ptr(rgb), _ptr(acc), _ptr(depth),
                                  _ptr(w), _ptr(tr), _stream()), "aon_composite")
@@ -357,7 +380,7 @@ def composite_backward(raw_rgb, raw_sigma, t_vals, dirs, weights, trans, g_rgb, 
     R, S = raw_sigma.shape[0], raw_sigma.shape[1]
     stride = 0 if t_vals.dim() == 1 else S
     g_raw_rgb, g_raw_sigma = torch.empty_like(raw_rgb), torch.empty_like(raw_sigma)
-    with torch.cuda.device(raw_rgb.device):
+    with _on(raw_rgb.device):
         _check(lib.aon_composite_backward(_ptr(raw_rgb, "raw_rgb"), _ptr(raw_sigma, "raw_sigma"), _ptr(t_vals, "t_vals"), stride,
                                           _ptr(dirs, "dirs"), _ptr(weights, "weights"), _ptr(trans, "trans"),
                                           _ptr(g_rgb, "g_rgb"), _ptr(g_acc, "g_acc"), _ptr(g_depth, "g_depth"), R, S,
@@ -370,10 +393,24 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, 
               beta1: float, beta2: float, eps: float, step: int, grad_scale: float = 1.0) -> None:
     """One Adam step over flat fp32 buffers, in place (torch.optim.Adam formulas)."""
     lib = load()
-    with torch.cuda.device(params.device):
+    with _on(params.device):
         _check(lib.aon_adam_step(_ptr(params, "params"), _ptr(grads, "grads"), _ptr(exp_avg, "exp_avg"),
                                  _ptr(exp_avg_sq, "exp_avg_sq"), params.numel(), float(lr), float(beta1), float(beta2),
                                  float(eps), int(step), float(grad_scale), _stream()), "aon_adam_step")
+
+
+def adam_scalars(lr: float, beta1: float, beta2: float, eps: float, step: int, grad_scale: float, out: torch.Tensor) -> None:
+    """the seven step-dependent floats of the Adam kernel into a HOST (pinned) float32 tensor [7]"""
+    _check(load().aon_adam_scalars(float(lr), float(beta1), float(beta2), float(eps), int(step), float(grad_scale),
+                                   C.cast(out.data_ptr(), C.POINTER(C.c_float))), "aon_adam_scalars")
+
+
+def adam_step_dev(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, scalars_dev: torch.Tensor) -> None:
+    """Adam step whose scalars live in device memory (graph-capturable)."""
+    lib = load()
+    with _on(params.device):
+        _check(lib.aon_adam_step_dev(_ptr(params, "params"), _ptr(grads, "grads"), _ptr(exp_avg, "exp_avg"), _ptr(exp_avg_sq, "exp_avg_sq"),
+                                     params.numel(), _ptr(scalars_dev, "scalars"), _stream()), "aon_adam_step_dev")
 
 
 # ---- training path, stage 2: tcgen05 GEMMs on packed 16-bit hi/lo planes (csrc/gemm_tc.cu) ---------------------
@@ -433,7 +470,7 @@ def pack_rows(src: torch.Tensor, M: int, m_tiles: int, c_pad: int, scale: float,
     if not (src.is_cuda and src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1):
         raise AonError("pack_rows: src must be a CUDA float32 [rows, C] tensor with contiguous rows")
     out = PK(m_tiles, c_pad, src.device, x3)
-    with torch.cuda.device(src.device):
+    with _on(src.device):
         _check(lib.aon_pack_rows(src.data_ptr(), src.stride(0), src.shape[1], M, row_div, m_tiles, c_pad, float(scale),
                                  out.hi.data_ptr(), _p(out.lo), _stream()), "aon_pack_rows")
     return out
@@ -442,7 +479,7 @@ def pack_rows(src: torch.Tensor, M: int, m_tiles: int, c_pad: int, scale: float,
 def pack_linear(W: torch.Tensor, transpose: bool, r_pad: int, k_pad: int, scale: float, x3: bool = True) -> PW:
     lib = load()
     out = PW(r_pad, k_pad, W.device, x3)
-    with torch.cuda.device(W.device):
+    with _on(W.device):
         _check(lib.aon_pack_linear(_ptr(W, "W"), W.shape[0], W.shape[1], int(transpose), r_pad, k_pad, float(scale),
                                    out.hi.data_ptr(), _p(out.lo), _stream()), "aon_pack_linear")
     return out
@@ -486,7 +523,7 @@ def gemm_nt(segs, N: int, m_tiles: int, device, *, epi: int = EPI_LINEAR, bias=N
     if colsum:
         cs = torch.empty(m_tiles, N, dtype=torch.float32, device=device)
         g.colsum = cs.data_ptr()
-    with torch.cuda.device(device):
+    with _on(device):
         _check(lib.aon_gemm_tc(C.byref(g), _stream()), "aon_gemm_tc(NT)")
     return cs
 
@@ -506,7 +543,7 @@ def gemm_tn(A: PK, a_off: int, a_tiles: int, B: PK, b_off: int, N: int, splits: 
     g.a_feat[0], g.a_off[0], g.b_feat[0], g.b_off[0] = A.feat, a_off, B.feat, b_off
     g.a_tiles, g.splits, g.tiles_per_split = a_tiles, splits, tps
     g.partial, g.inv_scale = part.data_ptr(), 1.0
-    with torch.cuda.device(A.hi.device):
+    with _on(A.hi.device):
         _check(lib.aon_gemm_tc(C.byref(g), _stream()), "aon_gemm_tc(TN)")
     return part
 
@@ -515,7 +552,7 @@ def wgrad_reduce(partial: torch.Tensor, scale: float, dst: torch.Tensor, col_off
                  transpose: bool = False) -> None:
     lib = load()
     splits, rows_pad, N = partial.shape
-    with torch.cuda.device(dst.device):
+    with _on(dst.device):
         _check(lib.aon_wgrad_reduce(partial.data_ptr(), splits, rows_pad, N, float(scale), _ptr(dst, "dst"), dst.stride(0), col_off,
                                     rows_valid, cols_valid, int(transpose), _stream()), "aon_wgrad_reduce")
 
@@ -525,7 +562,7 @@ def colsum_packed(x: PK, splits: int = 16) -> torch.Tensor:
     lib = load()
     splits = max(1, min(splits, x.m_tiles))
     part = torch.empty(splits, x.feat, dtype=torch.float32, device=x.hi.device)
-    with torch.cuda.device(x.hi.device):
+    with _on(x.hi.device):
         _check(lib.aon_colsum_packed(x.hi.data_ptr(), _p(x.lo), x.feat, x.m_tiles, splits, part.data_ptr(), _stream()),
                "aon_colsum_packed")
     return part

@@ -46,16 +46,37 @@ def _hp(hparams) -> SimpleNamespace:
     return SimpleNamespace(**d)
 
 
+class _Logged(dict):
+    """name -> float, converted lazily: ``log()`` stores the device scalar as it is (no host synchronisation inside
+    training_step -- three ``float()`` calls per step would stall the launch queue three times); reading an entry converts."""
+
+    def __getitem__(self, k):
+        v = dict.__getitem__(self, k)
+        if torch.is_tensor(v):
+            v = float(v)
+            dict.__setitem__(self, k, v)
+        return v
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in list(self.keys())]
+
+    def values(self):
+        return [self[k] for k in list(self.keys())]
+
+
 class LitModel(nn.Module):
     """models/interface.py:22-62 -- the parts the render path touches (logging + PSNR)."""
 
     def __init__(self):
         super().__init__()
-        self.logged: Dict[str, float] = {}
+        self.logged: Dict[str, float] = _Logged()
         self.trainer = SimpleNamespace(global_step=0, is_global_zero=True)
 
     def log(self, name, value, **_):
-        self.logged[name] = float(value)
+        self.logged[name] = value.detach() if torch.is_tensor(value) else float(value)
 
     @torch.no_grad()
     def psnr_legacy(self, pred: Tensor, gt: Tensor) -> Tensor:
@@ -106,6 +127,7 @@ class FlatAdam(torch.optim.Optimizer):
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.steps, self.grad_scale = 0, 1.0
+        self.scalars_dev = None           # set by GraphedStep: the Adam scalars come from device memory (graph-capturable step)
         off = 0
         with torch.no_grad():
             for p in ps:
@@ -132,8 +154,11 @@ class FlatAdam(torch.optim.Optimizer):
                 loss = closure()
         g = self.param_groups[0]
         self.steps += 1
-        L.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1],
-                    g["eps"], self.steps, self.grad_scale)
+        if self.scalars_dev is not None:
+            L.adam_step_dev(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.scalars_dev)
+        else:
+            L.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1],
+                        g["eps"], self.steps, self.grad_scale)
         for p in g["params"]:                           # the kernel wrote through raw pointers: tell autograd / the
             torch.autograd.graph.increment_version(p)   # packed-weight cache that the values changed
         return loss
@@ -205,6 +230,119 @@ class GradSync:
         for w in self.works:
             w.wait()
         return 1.0 / self.world
+
+
+class GraphedStep:
+    """One training step -- zero_grad, training_step, backward, (gradient all-reduces), optimizer_step -- captured ONCE in a
+    CUDA graph and replayed: a vanilla step is ~300 kernel launches whose host-side enqueue (7.4 ms) is almost as long as
+    their execution; a replay costs microseconds of host time.  Shapes must not change between steps (the reference's
+    fixed-size ray batches, model.py:421-428 / sapien_multi.py:235).  The batch is copied into static buffers; the learning
+    rate / bias corrections reach the Adam kernel through a 7-float device buffer refreshed before every replay
+    (aon_adam_step_dev), because a graph bakes kernel arguments in.  torch's CUDA generator is graph-aware, so the stratified
+    and inverse-cdf draws differ from replay to replay as they must."""
+
+    RING = 64
+
+    def __init__(self, system, opt, batch, sync: "GradSync" = None, warmup: int = 3):
+        self.system, self.opt, self.sync = system, opt, sync
+        self.static = {k: (v.clone() if torch.is_tensor(v) and v.is_cuda else v) for k, v in batch.items()}
+        dev = opt.flat.device
+        # the host runs many replays ahead of the device, and an asynchronous copy reads its pinned source when it EXECUTES:
+        # every step gets its own slot of a ring, and a slot is reused only after the copy that read it has completed
+        self.sc_ring = torch.zeros(self.RING, 7, dtype=torch.float32).pin_memory()
+        self.sc_events = [None] * self.RING
+        self.sc_slot = 0
+        self.sc_dev = torch.zeros(7, dtype=torch.float32, device=dev)
+        opt.scalars_dev = self.sc_dev
+        self.graph = None
+        self.loss = None
+        # DRY RUN: warm-up steps on a side stream (allocator pools, lazily created handles, tensor-map cache) and the capture
+        # itself must not count as training -- parameters, Adam moments, step counters and the generator state are restored
+        # afterwards, so the first replay is the first real step on this batch
+        saved = (opt.flat.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.steps, system.trainer.global_step,
+                 torch.cuda.get_rng_state(dev))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._refresh_scalars()
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        self._refresh_scalars()
+        n0 = L.launch_count()
+        try:
+            with torch.cuda.graph(g):
+                self._body()
+            self.launches = L.launch_count() - n0  # kernels of THIS library inside one replay (ATen's come on top)
+            self.graph = g
+        finally:
+            # also after a failed capture (e.g. the caller keeps an autograd graph alive whose AccumulateGrad nodes belong to
+            # another stream): the dry run must leave no trace, and the caller falls back to eager steps
+            torch.cuda.synchronize()
+            with torch.no_grad():
+                opt.flat.copy_(saved[0]); opt.exp_avg.copy_(saved[1]); opt.exp_avg_sq.copy_(saved[2])
+            opt.steps, system.trainer.global_step = saved[3], saved[4]
+            torch.cuda.set_rng_state(saved[5], dev)
+            for p in opt.param_groups[0]["params"]:
+                torch.autograd.graph.increment_version(p)
+            if self.graph is None:
+                opt.scalars_dev = None
+                try:        # a capture that failed half-way leaves torch's CUDA generator in "capturing" state (its next
+                    with torch.cuda.graph(torch.cuda.CUDAGraph()):      # eager draw raises); a tiny complete capture resets it
+                        torch.rand(1, device=dev)
+                    torch.cuda.set_rng_state(saved[5], dev)
+                except Exception:
+                    pass
+
+    def _refresh_scalars(self):
+        system, opt = self.system, self.opt
+        lr = system.learning_rate(system.trainer.global_step)
+        for pg in opt.param_groups:
+            pg["lr"] = lr
+        g = opt.param_groups[0]
+        scale = 1.0 / self.sync.world if (self.sync is not None and self.sync.world > 1) else 1.0
+        i = self.sc_slot
+        self.sc_slot = (i + 1) % self.RING
+        if self.sc_events[i] is not None:
+            self.sc_events[i].synchronize()
+        L.adam_scalars(lr, g["betas"][0], g["betas"][1], g["eps"], opt.steps + 1, scale, self.sc_ring[i])
+        self.sc_dev.copy_(self.sc_ring[i], non_blocking=True)
+        if self.sc_events[i] is None:
+            self.sc_events[i] = torch.cuda.Event()
+        self.sc_events[i].record()
+
+    def _body(self):
+        system, opt = self.system, self.opt
+        opt.zero_grad(set_to_none=False)
+        if self.sync is not None:
+            self.sync.start()
+        loss = system.training_step(self.static, 0)
+        loss.backward()
+        # keep only the VALUE: a live reference to the loss keeps this iteration's autograd graph -- and its AccumulateGrad
+        # nodes, which are bound to the stream they were created on -- alive; the capture would then accumulate gradients on
+        # the warm-up stream, outside the graph
+        self.loss = loss.detach()
+        del loss
+        if self.sync is not None:
+            self.sync.finish()
+        opt.step()
+
+    def _advance(self):
+        self.system.trainer.global_step += 1
+
+    def __call__(self, batch) -> Tensor:
+        for k, v in batch.items():
+            if torch.is_tensor(v) and v.is_cuda:
+                self.static[k].copy_(v, non_blocking=True)
+        self._refresh_scalars()
+        self.opt.steps += 1                   # the captured opt.step() does not run Python on replay
+        self.graph.replay()
+        for p in self.opt.param_groups[0]["params"]:
+            torch.autograd.graph.increment_version(p)
+        self._advance()
+        return self.loss
 
 
 class _LitCommon(LitModel):
@@ -394,8 +532,10 @@ class Trainer:
     process per GPU.  Training gradients are averaged across ranks with ONE flat all-reduce per step
     (DDP semantics of run.py:109; dist.allreduce_mean_)."""
 
-    def __init__(self, max_steps: int = 1000, log_every: int = 0):
+    def __init__(self, max_steps: int = 1000, log_every: int = 0, cuda_graph: Optional[bool] = None):
         self.max_steps, self.log_every = max_steps, log_every
+        # replay the step as a CUDA graph (GraphedStep); default: on for the tcgen05 training paths, AON_TRAIN_GRAPH=0/1 overrides
+        self.cuda_graph = cuda_graph if cuda_graph is not None else os.environ.get("AON_TRAIN_GRAPH", "1") == "1"
         self.global_step = 0
         self.is_global_zero = D.world()[0] == 0
         self.ckpt_every, self.on_checkpoint = 0, None     # periodic checkpoints (run.py sets both on rank 0)
@@ -424,16 +564,31 @@ class Trainer:
         sync = getattr(system, "_grad_sync", None)
         if sync is None:
             sync = system._grad_sync = GradSync(list(system.named_parameters()), opt.flat_grad)
+        graphed, shapes = None, None
+        use_graph = self.cuda_graph and sync.world == 1 and getattr(system.model, "train_gemm", "torch") in ("tc", "tc16")
         for batch_idx, batch in enumerate(batches):
             if self.global_step >= self.max_steps:
                 break
-            opt.zero_grad(set_to_none=False)
-            sync.start()
-            loss = system.training_step(batch, batch_idx)
-            loss.backward()                              # the fine MLP's gradient slice is all-reduced while the coarse MLP's backward runs
-            opt.grad_scale = sync.finish()
-            system.optimizer_step(0, batch_idx, opt, 0, None, False, False, False)
-            self.global_step += 1
+            if use_graph:
+                sig = tuple((k, tuple(v.shape)) for k, v in sorted(batch.items()) if torch.is_tensor(v))
+                if graphed is None or sig != shapes:
+                    try:
+                        graphed, shapes = GraphedStep(system, opt, batch, None), sig   # dry run + capture; trains nothing
+                    except Exception as e:       # capture refused (see GraphedStep): eager steps from here on
+                        if self.is_global_zero:
+                            print("lit.Trainer: CUDA-graph capture of the training step failed (%s: %s); running eager steps"
+                                  % (type(e).__name__, str(e).splitlines()[0]), flush=True)
+                        use_graph, graphed = False, None
+                if graphed is not None:
+                    graphed(batch)
+            if not use_graph:
+                opt.zero_grad(set_to_none=False)
+                sync.start()
+                loss = system.training_step(batch, batch_idx)
+                loss.backward()                          # the fine MLP's gradient slice is all-reduced while the coarse MLP's backward runs
+                opt.grad_scale = sync.finish()
+                system.optimizer_step(0, batch_idx, opt, 0, None, False, False, False)
+                self.global_step += 1
             if self.log_every and self.global_step % self.log_every == 0:
                 # the fp16 hi+lo operand planes of the training GEMMs saturate instead of overflowing; a non-finite gradient
                 # (or loss) means the power-of-two operand scaling of train_tc.py does not fit this model / loss: fail loudly

@@ -394,8 +394,19 @@ def train_block(args, dev, world, rank, rays_o, rays_d, gemm="tc"):
         batch.update(instance_id=torch.tensor([0], device=dev), articulation_id=torch.tensor([3], device=dev))
 
     sync = lit.GradSync(list(s.named_parameters()), opt.flat_grad)   # per-MLP slices all-reduced while the backward still runs
+    # one rank: the whole step (zero_grad .. Adam) is captured once in a CUDA graph and replayed (lit.GraphedStep), like
+    # lit.Trainer.fit does; several ranks: eager launches with the overlapped all-reduces
+    graphed = None
+    if world == 1 and os.environ.get("AON_TRAIN_GRAPH", "1") == "1":
+        try:
+            graphed = lit.GraphedStep(s, opt, batch, None)
+        except Exception as e:
+            sys.stderr.write("bench: CUDA-graph capture of the training step failed (%s); eager steps\n" % str(e).splitlines()[0])
 
     def step(i):
+        if graphed is not None:
+            graphed(batch)
+            return
         opt.zero_grad()
         sync.start()
         loss = s.training_step(batch, i)
@@ -423,7 +434,9 @@ def train_block(args, dev, world, rank, rays_o, rays_d, gemm="tc"):
             "rays_per_gpu_per_step": Rb, "steps": K, "warmup": 3, "algorithmic_tflops_per_gpu": flop / (ms * 1e-3) / 1e12,
             "gemm": {"tc": "tcgen05 kind::f16, fp16 hi+lo operands (3 MMAs per K step), fp32 accumulate",
                      "tc16": "tcgen05 kind::f16, single fp16 operand planes (1 MMA per K step; fast training mode, ~1e-3 gradient noise), fp32 accumulate"}.get(s.model.train_gemm, "library"),
-            "aon_launches_per_step": L.launch_count() // K, "grad_allreduce_bytes": opt.flat_grad.numel() * 4 if world > 1 else 0,
+            "aon_launches_per_step": graphed.launches if graphed is not None else L.launch_count() // K,
+            "cuda_graph": graphed is not None,
+            "grad_allreduce_bytes": opt.flat_grad.numel() * 4 if world > 1 else 0,
             "grad_allreduce": "%d asynchronous all-reduces per step (fine MLP, coarse MLP%s), launched from post-accumulate hooks while the "
                               "backward runs" % (len(sync.groups), ", code tables" if len(sync.groups) > 2 else "") if world > 1 else "none (1 rank)"}
 

@@ -212,6 +212,14 @@ int aon_composite_backward(const float* raw_rgb, const float* raw_sigma, const f
 int aon_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n,
                   double lr, double beta1, double beta2, double eps, long step, double grad_scale,
                   aon_stream_t stream);
+/* The same step with its seven step-dependent scalars (1-beta1, beta2, 1-beta2, eps, lr/bias_corr1, sqrt(bias_corr2),
+ * grad_scale) read from DEVICE memory, for a training step captured in a CUDA graph (kernel arguments are baked into a
+ * graph; the schedule is not): aon_adam_scalars fills the seven floats on the host exactly as aon_adam_step computes them,
+ * the caller copies them to scalars7_dev before every replay. */
+int aon_adam_scalars(double lr, double beta1, double beta2, double eps, long step, double grad_scale,
+                     float* out7_host);
+int aon_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n,
+                      const float* scalars7_dev, aon_stream_t stream);
 
 /* ---- training path, stage 2: tcgen05 GEMMs for the MLP's forward / dgrad / wgrad (csrc/gemm_tc.cu) ------------
  * Replaces the nn.Linear contractions of NeRFMLP.forward (model.py:99-118) and their autograd adjoints in

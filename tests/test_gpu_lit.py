@@ -55,3 +55,38 @@ def test_lit_eval_and_train(built_lib, exp):
         losses.append(s.logged["train/loss"])
         tr.max_steps += 8
     assert losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("exp", ["vanilla", "vanilla_autodecoder"])
+def test_graphed_step_equals_eager(built_lib, exp):
+    """lit.Trainer replays the training step as a CUDA graph (lit.GraphedStep: static batch buffers, Adam scalars through
+    device memory, dry-run capture).  With the random draws switched off the replayed steps must leave EXACTLY the parameters
+    the eager loop leaves: same kernels, deterministic reductions, same learning-rate schedule, capture trains nothing."""
+    from aon_b200 import lit
+    dev = torch.device("cuda:0")
+    rays = {k: v.to(dev) for k, v in O.sapien_rays(24, 32, seed=5).items()}
+    g = torch.Generator().manual_seed(1)
+    target = torch.rand(rays["rays_o"].shape[0], 3, generator=g).to(dev)
+
+    def batches():
+        for i in range(6):                                   # six different 128-ray batches
+            sl = slice(128 * i, 128 * (i + 1))
+            b = {k: v[sl][None] for k, v in rays.items()}
+            b["target"] = target[sl][None]
+            if exp != "vanilla":
+                b.update(instance_id=torch.tensor([0], device=dev), articulation_id=torch.tensor([i % 10], device=dev))
+            yield b
+
+    flats = []
+    for graph in (False, True):
+        torch.manual_seed(0)
+        s = lit.build_system(_hp(exp)).to(dev)
+        s.randomized = False
+        s.lr_delay_steps = 4                                 # the learning rate changes every step
+        tr = lit.Trainer(max_steps=6, cuda_graph=graph)
+        tr.fit(s, batches())
+        assert tr.global_step == 6 and s._optimizer.steps == 6
+        flats.append((s._optimizer.flat.clone(), s._optimizer.exp_avg_sq.clone(), s.logged["train/loss"]))
+    assert torch.equal(flats[0][0], flats[1][0]), (flats[0][0] - flats[1][0]).abs().max().item()
+    assert torch.equal(flats[0][1], flats[1][1])
+    assert flats[0][2] == flats[1][2]

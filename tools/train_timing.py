@@ -16,8 +16,9 @@ from aon_b200 import lib as L, lit, synth
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=20)
-args = ap.parse_args()
 dev = torch.device("cuda:0")
+ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph replay of lit.GraphedStep")
+args = ap.parse_args()
 for exp, R, gemm in (("vanilla", 2048, "tc"), ("vanilla_autodecoder", 4096, "tc"), ("vanilla", 2048, "tc16"), ("vanilla_autodecoder", 4096, "tc16")):
     torch.manual_seed(0)
     s = lit.build_system(SimpleNamespace(exp_type=exp, run_max_steps=1000, white_back=True, N_max_objs=1, N_obj_code_length=128)).to(dev)
@@ -31,7 +32,11 @@ for exp, R, gemm in (("vanilla", 2048, "tc"), ("vanilla_autodecoder", 4096, "tc"
     opt = s.configure_optimizers()
     s.trainer = SimpleNamespace(global_step=0, is_global_zero=True)
 
+    graphed = None if args.no_graph else lit.GraphedStep(s, opt, batch, None)
+
     def step(i):
+        if graphed is not None:
+            return graphed(batch)
         opt.zero_grad()
         loss = s.training_step(batch, i)
         loss.backward()
@@ -44,12 +49,21 @@ for exp, R, gemm in (("vanilla", 2048, "tc"), ("vanilla_autodecoder", 4096, "tc"
     L.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    import time
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    for i in range(2):               # 2 steps = ~600 launches: below the launch queue depth, so this is pure host cost
+        step(i)
+    t_host2 = (time.perf_counter() - t2) / 2 * 1e3
+    torch.cuda.synchronize()
     e0.record()
+    t_host = time.perf_counter()
     for i in range(args.steps):
         loss = step(i)
-    e1.record()
+    t_host = (time.perf_counter() - t_host) / args.steps * 1e3      # host time to ENQUEUE a step (no sync inside the loop ...
+    e1.record()                                                      # ... except the float() of the logged scalars)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     flop = 3 * R * 258 * (1186816 if exp == "vanilla" else 1589760)
-    print("%-20s %-4s %5d rays/step: %.2f ms/step -> %.0f rays/s training, %.1f algorithmic TFLOP/s (fwd+bwd = 3x fwd), "
-          "%d aon kernel launches/step, loss %.4f" % (exp, gemm, R, ms, R / ms * 1e3, flop / ms * 1e-9, L.launch_count() // args.steps, loss.item()))
+    print("%-20s %-4s %-5s %5d rays/step: %.2f ms/step -> %.0f rays/s training, %.1f algorithmic TFLOP/s (fwd+bwd = 3x fwd), "
+          "%d aon kernel launches/step, host enqueue %.2f ms/step (%.2f ms/step with an empty launch queue), loss %.4f" % (exp, gemm, "eager" if graphed is None else "graph", R, ms, R / ms * 1e3, flop / ms * 1e-9, L.launch_count() // (args.steps + 2), t_host, t_host2, loss.item()))
