@@ -162,22 +162,23 @@ __global__ void raygen_kernel(int H, int W, float focal, Cam c, float* __restric
 
 // ---- A3 coarse sampling -------------------------------------------------------------------------------
 __global__ void sample_along_rays_kernel(float near, float far, int n, const float* __restrict__ t_rand,
-                                         int R, float* __restrict__ t_vals) {
-  const long total = t_rand ? (long)R * n : n;
+                                         int R, float* __restrict__ t_vals, RngDev rng) {
+  const long total = (t_rand || rng.on) ? (long)R * n : n;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
        idx += (long)gridDim.x * blockDim.x) {
     const int i = (int)(idx % n);
     const float t = coarse_t(i, n, near, far);
-    if (!t_rand) {
+    if (!t_rand && !rng.on) {
       t_vals[idx] = t;
       continue;
     }
+    const float draw = t_rand ? t_rand[idx] : rng_uniform(rng, RNG_STREAM_STRATIFIED, (unsigned)(idx / n), (unsigned)i);
     // helper.py:122-127: stratified jitter between midpoints
     const float tp = i > 0 ? coarse_t(i - 1, n, near, far) : t;
     const float tn = i < n - 1 ? coarse_t(i + 1, n, near, far) : t;
     const float lower = i > 0 ? __fmul_rn(0.5f, __fadd_rn(t, tp)) : t;
     const float upper = i < n - 1 ? __fmul_rn(0.5f, __fadd_rn(tn, t)) : t;
-    t_vals[idx] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand[idx]));
+    t_vals[idx] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), draw));
   }
 }
 
@@ -188,13 +189,21 @@ constexpr int PDF_WARPS = 8;
 __global__ void __launch_bounds__(PDF_WARPS * 32)
 sample_pdf_kernel(const float* __restrict__ t_coarse, long t_stride, const float* __restrict__ weights,
                   const float* __restrict__ u_in, long u_stride, int R, int nc, int nf,
-                  float* __restrict__ t_fine) {
+                  float* __restrict__ t_fine, RngDev rng) {
   __shared__ float s_scr[PDF_WARPS][PDF_SCRATCH_FLOATS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (long ray = (long)blockIdx.x * PDF_WARPS + warp; ray < R; ray += (long)gridDim.x * PDF_WARPS)
     sample_pdf_ray<false>(t_coarse + ray * t_stride, weights + ray * (long)nc, u_in ? u_in + ray * u_stride : nullptr, nc, nf,
-                          s_scr[warp], t_fine + ray * (long)(nc + nf), lane);
+                          s_scr[warp], t_fine + ray * (long)(nc + nf), lane, &rng, (unsigned)ray);
 }
+
+// the draws themselves, [rows, cols] of one stream (tests, debugging: the sampling kernels never materialise them)
+__global__ void rng_uniform_kernel(RngDev rng, unsigned stream, int rows, int cols, float* __restrict__ out) {
+  const long total = (long)rows * cols;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x)
+    out[idx] = rng_uniform(rng, stream, (unsigned)(idx / cols), (unsigned)(idx % cols));
+}
+__global__ void rng_advance_kernel(unsigned long long* offset_dev, unsigned long long by) { *offset_dev += by; }
 
 // rays of pixels [p0, p0 + n) of an H x W view (tail of a fused image render that takes the three-launch path)
 __global__ void raygen_range_kernel(int H, int W, float focal, Cam c, long p0, int n, float* __restrict__ rays_o,
@@ -347,18 +356,66 @@ int aon_raygen(int H, int W, float focal, const float* c2w_host, float* rays_o, 
   return AON_OK;
 }
 
-int aon_sample_along_rays(float near, float far, int n_points, const float* t_rand, int R,
-                          float* t_vals, aon_stream_t stream) {
-  AON_REQUIRE(n_points >= 2 && t_vals && (t_rand == nullptr || R > 0), "aon_sample_along_rays: bad argument");
-  const long total = t_rand ? (long)R * n_points : n_points;
+static RngDev rng_dev(const AonRng* r) {
+  RngDev g;
+  g.seed = r ? r->seed : 0; g.offset = r ? r->offset : 0; g.offset_dev = r ? r->offset_dev : nullptr; g.on = r != nullptr;
+  return g;
+}
+
+static int sample_along_rays_impl(float near, float far, int n_points, const float* t_rand, const AonRng* rng, int R,
+                                  float* t_vals, aon_stream_t stream) {
+  const bool per_ray = t_rand != nullptr || rng != nullptr;
+  AON_REQUIRE(n_points >= 2 && t_vals && (!per_ray || R > 0), "aon_sample_along_rays: bad argument");
+  const long total = per_ray ? (long)R * n_points : n_points;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  sample_along_rays_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(near, far, n_points, t_rand, R, t_vals);
+  sample_along_rays_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(near, far, n_points, t_rand, R, t_vals, rng_dev(rng));
   AON_LAUNCH_CHECK();
   return AON_OK;
 }
 
+int aon_sample_along_rays(float near, float far, int n_points, const float* t_rand, int R,
+                          float* t_vals, aon_stream_t stream) {
+  return sample_along_rays_impl(near, far, n_points, t_rand, nullptr, R, t_vals, stream);
+}
+
+int aon_sample_along_rays_rng(float near, float far, int n_points, const AonRng* rng, int R, float* t_vals, aon_stream_t stream) {
+  AON_REQUIRE(rng != nullptr, "aon_sample_along_rays_rng: null rng");
+  return sample_along_rays_impl(near, far, n_points, nullptr, rng, R, t_vals, stream);
+}
+
+int aon_rng_uniform(const AonRng* rng, int stream_id, int rows, int cols, float* out, aon_stream_t stream) {
+  AON_REQUIRE(rng && out && rows >= 0 && cols >= 1 && (stream_id == 0 || stream_id == 1), "aon_rng_uniform: bad argument");
+  if (rows == 0) return AON_OK;
+  const long total = (long)rows * cols;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  rng_uniform_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rng_dev(rng), (unsigned)stream_id, rows, cols, out);
+  AON_LAUNCH_CHECK();
+  return AON_OK;
+}
+
+int aon_rng_advance(unsigned long long* offset_dev, unsigned long long by, aon_stream_t stream) {
+  AON_REQUIRE(offset_dev != nullptr, "aon_rng_advance: null pointer");
+  rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(offset_dev, by);
+  AON_LAUNCH_CHECK();
+  return AON_OK;
+}
+
+static int sample_pdf_impl(const float* t_coarse, long t_stride, const float* weights, const float* u, long u_stride,
+                           const AonRng* rng, int R, int n_coarse, int n_fine, float* t_fine, aon_stream_t stream);
+
 int aon_sample_pdf(const float* t_coarse, long t_stride, const float* weights, const float* u,
                    long u_stride, int R, int n_coarse, int n_fine, float* t_fine, aon_stream_t stream) {
+  return sample_pdf_impl(t_coarse, t_stride, weights, u, u_stride, nullptr, R, n_coarse, n_fine, t_fine, stream);
+}
+
+int aon_sample_pdf_rng(const float* t_coarse, long t_stride, const float* weights, const AonRng* rng, int R, int n_coarse,
+                       int n_fine, float* t_fine, aon_stream_t stream) {
+  AON_REQUIRE(rng != nullptr, "aon_sample_pdf_rng: null rng");
+  return sample_pdf_impl(t_coarse, t_stride, weights, nullptr, 0, rng, R, n_coarse, n_fine, t_fine, stream);
+}
+
+static int sample_pdf_impl(const float* t_coarse, long t_stride, const float* weights, const float* u, long u_stride,
+                           const AonRng* rng, int R, int n_coarse, int n_fine, float* t_fine, aon_stream_t stream) {
   AON_REQUIRE(t_coarse && weights && t_fine, "aon_sample_pdf: null pointer");
   AON_REQUIRE(R >= 0 && n_coarse >= 4 && n_coarse <= PDF_MAX_COARSE && n_fine >= 1 && n_fine <= PDF_MAX_FINE,
               "aon_sample_pdf: unsupported sizes R=%d n_coarse=%d n_fine=%d", R, n_coarse, n_fine);
@@ -366,7 +423,7 @@ int aon_sample_pdf(const float* t_coarse, long t_stride, const float* weights, c
   if (R == 0) return AON_OK;
   const int blocks = (R + PDF_WARPS - 1) / PDF_WARPS;
   sample_pdf_kernel<<<blocks < 148 * 8 ? blocks : 148 * 8, PDF_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      t_coarse, t_stride, weights, u, u_stride, R, n_coarse, n_fine, t_fine);
+      t_coarse, t_stride, weights, u, u_stride, R, n_coarse, n_fine, t_fine, rng_dev(rng));
   AON_LAUNCH_CHECK();
   return AON_OK;
 }

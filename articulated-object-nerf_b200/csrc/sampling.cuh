@@ -43,6 +43,37 @@ __device__ __forceinline__ float coarse_t(int i, int n, float near, float far) {
   return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, s)), __fmul_rn(far, s));
 }
 
+// ---- in-kernel random draws (helper.py:126 stratified jitter, helper.py:227 inverse-cdf draws) -----------------------------
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; the generator behind torch.rand on CUDA),
+// used as a pure FUNCTION of (seed, step offset, stream, row, column): a draw does not depend on the launch shape, so no
+// [R,65] / [R,128] tensor of uniforms is ever written to HBM and a CUDA-graph replay only needs the step offset to advance
+// in device memory.  key = seed (lo, hi); counter = (column / 4, row, offset lo, offset hi[0:30) | stream << 30); the draw of
+// column c is word c % 4 of the block, mapped to [0, 1) as (x >> 8) * 2^-24.  oracle/philox.py restates it in numpy.
+struct RngDev {
+  unsigned long long seed, offset;
+  const unsigned long long* offset_dev;   // optional: added to `offset` (the step counter of a captured training step)
+  int on;
+};
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float rng_uniform(const RngDev& g, unsigned stream, unsigned row, unsigned col) {
+  const unsigned long long off = g.offset + (g.offset_dev ? *g.offset_dev : 0ull);
+  const uint4 c = make_uint4(col >> 2, row, (unsigned)off, ((unsigned)(off >> 32) & 0x3FFFFFFFu) | (stream << 30));
+  const uint4 x = philox4x32_10(c, make_uint2((unsigned)g.seed, (unsigned)(g.seed >> 32)));
+  const unsigned w = (col & 3u) == 0 ? x.x : (col & 3u) == 1 ? x.y : (col & 3u) == 2 ? x.z : x.w;
+  return (float)(w >> 8) * 5.9604644775390625e-08f;   // 2^-24: [0, 1)
+}
+constexpr unsigned RNG_STREAM_STRATIFIED = 0, RNG_STREAM_INVERSE_CDF = 1;
+
 constexpr int PDF_MAX_COARSE = 65;
 constexpr int PDF_MAX_FINE = 128;
 constexpr int PDF_ST_FLOATS = PDF_MAX_COARSE + PDF_MAX_FINE + 3;   // per-warp scratch: values to sort
@@ -75,7 +106,8 @@ __device__ __forceinline__ float aten_row_sum(const float* x, int n, int lane) {
 
 // Hierarchical sampling of ONE ray by ONE warp: helper.py:203-252 + model.py:162-166.
 //   tc [nc] coarse t of the ray; w [nc] compositing weights (the first and last are dropped here, model.py:165);
-//   u [nf] inverse-cdf draws or nullptr = the deterministic table of helper.py:229; out [nc + nf] sorted.
+//   u [nf] inverse-cdf draws or nullptr = the deterministic table of helper.py:229 (or, with rng->on, draws generated here);
+//   out [nc + nf] sorted.
 //   scr: PDF_SCRATCH_FLOATS floats of shared memory owned by this warp.
 // The bracket search (idx = #{cdf <= u}) is bit-equivalent to the reference's mask-max/min formulation
 // (oracle: sorted_piecewise_constant_pdf_bracket); the reference's sort of the concatenated [t_coarse | samples] is a
@@ -84,7 +116,8 @@ __device__ __forceinline__ float aten_row_sum(const float* x, int n, int lane) {
 template <bool STREAM_LD>
 __device__ __forceinline__ void sample_pdf_ray(const float* __restrict__ tc, const float* __restrict__ w,
                                                const float* __restrict__ u_in, int nc, int nf, float* scr,
-                                               float* __restrict__ out, int lane) {
+                                               float* __restrict__ out, int lane, const RngDev* rng = nullptr,
+                                               unsigned rng_row = 0) {
   float* st = scr;
   float* sb = scr + PDF_ST_FLOATS;
   float* sc = sb + PDF_MAX_COARSE;
@@ -121,6 +154,8 @@ __device__ __forceinline__ void sample_pdf_ray(const float* __restrict__ tc, con
     float u;
     if (u_in) {
       u = u_in[j];
+    } else if (rng != nullptr && rng->on) {
+      u = rng_uniform(*rng, RNG_STREAM_INVERSE_CDF, rng_row, (unsigned)j);   // helper.py:227: torch.rand(..., num_samples)
     } else {
       // helper.py:229: linspace(0, 1 - 2^-32, nf); the end point rounds to 1.0f
       u = linspace01(j, nf, 1.0f);

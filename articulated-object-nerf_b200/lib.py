@@ -33,9 +33,13 @@ SYMBOLS = {
     "aon_fold_latents": (_i, [_i, _i, _vp, _fp, _fp, _fp, _fp, _vp]),
     "aon_raygen": (_i, [_i, _i, _f, C.POINTER(_f), _fp, _fp, _vp]),
     "aon_sample_along_rays": (_i, [_f, _f, _i, _fp, _i, _fp, _vp]),
+    "aon_sample_along_rays_rng": (_i, [_f, _f, _i, _vp, _i, _fp, _vp]),
+    "aon_rng_uniform": (_i, [_vp, _i, _i, _i, _fp, _vp]),
+    "aon_rng_advance": (_i, [_vp, C.c_ulonglong, _vp]),
     "aon_workspace_bytes": (_sz, [_i, _i]),
     "aon_render_level": (_i, [_i, _i, _vp, _fp, _fp, _fp, _fp, _fp, _l, _i, _i, _i, _fp, _fp, _fp, _fp, _vp, _sz, _vp, _vp]),
     "aon_sample_pdf": (_i, [_fp, _l, _fp, _fp, _l, _i, _i, _i, _fp, _vp]),
+    "aon_sample_pdf_rng": (_i, [_fp, _l, _fp, _vp, _i, _i, _i, _fp, _vp]),
     "aon_render_rays": (_i, [_i, _i, _vp, _vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _f, _f, _i, _fp, _fp, _vp, _sz, _vp, _vp]),
     "aon_render_image": (_i, [_i, _i, _vp, _vp, _fp, _fp, C.POINTER(_f), _f, _i, _i, _l, _i, _f, _f, _i, _fp, _fp, _vp, _sz, _vp, _vp]),
     "aon_render_image_host": (_i, [_i, _i, _vp, _vp, _fp, _fp, _fp, _fp, _fp, _i, _f, _f, _i, _fp, _fp, _vp, _sz, _vp, _vp]),
@@ -182,14 +186,50 @@ def raygen(H: int, W: int, focal: float, c2w, device) -> tuple:
     return o, d
 
 
-def sample_along_rays(near: float, far: float, n_points: int, R: int, device, t_rand: Optional[torch.Tensor] = None):
-    """A3: deterministic -> shared table [n_points]; with t_rand [R,n_points] -> [R,n_points]."""
+class AonRng(C.Structure):
+    """Mirror of `struct AonRng` in include/aon.h."""
+    _fields_ = [("seed", C.c_ulonglong), ("offset", C.c_ulonglong), ("offset_dev", _vp)]
+
+
+class Rng:
+    """State of the in-kernel Philox draws: a 64-bit seed and a step offset that lives in DEVICE memory (one int64), so a
+    training step captured in a CUDA graph advances it by itself (aon_rng_advance inside the graph)."""
+
+    def __init__(self, seed: int, device):
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.offset_dev = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def struct(self, offset: int = 0) -> AonRng:
+        return AonRng(self.seed, int(offset), self.offset_dev.data_ptr())
+
+    def advance(self, by: int = 1) -> None:
+        with _on(self.offset_dev.device):
+            _check(load().aon_rng_advance(self.offset_dev.data_ptr(), int(by), _stream()), "aon_rng_advance")
+
+    def uniform(self, stream_id: int, rows: int, cols: int) -> torch.Tensor:
+        """the draws [rows, cols] of stream 0 (stratified) / 1 (inverse cdf) at the current offset -- tests and debugging"""
+        out = torch.empty(rows, cols, dtype=torch.float32, device=self.offset_dev.device)
+        with _on(out.device):
+            r = self.struct()
+            _check(load().aon_rng_uniform(C.byref(r), stream_id, rows, cols, _ptr(out), _stream()), "aon_rng_uniform")
+        return out
+
+
+def sample_along_rays(near: float, far: float, n_points: int, R: int, device, t_rand: Optional[torch.Tensor] = None,
+                      rng: Optional[Rng] = None):
+    """A3: deterministic -> shared table [n_points]; with t_rand [R,n_points] (or rng: draws generated in the kernel)
+    -> [R,n_points]."""
     lib = load()
-    shape = (n_points,) if t_rand is None else (R, n_points)
+    shape = (n_points,) if (t_rand is None and rng is None) else (R, n_points)
     t = torch.empty(shape, dtype=torch.float32, device=device)
     with _on(t.device):
-        _check(lib.aon_sample_along_rays(float(near), float(far), n_points, _ptr(t_rand, "t_rand"), R, _ptr(t), _stream()),
-               "aon_sample_along_rays")
+        if rng is not None and t_rand is None:
+            r = rng.struct()
+            _check(lib.aon_sample_along_rays_rng(float(near), float(far), n_points, C.byref(r), R, _ptr(t), _stream()),
+                   "aon_sample_along_rays_rng")
+        else:
+            _check(lib.aon_sample_along_rays(float(near), float(far), n_points, _ptr(t_rand, "t_rand"), R, _ptr(t), _stream()),
+                   "aon_sample_along_rays")
     return t
 
 
@@ -254,14 +294,21 @@ def render_level(kind: int, precision: int, packed: torch.Tensor, folded: Option
     return rgb, acc, depth, w
 
 
-def sample_pdf(t_coarse: torch.Tensor, weights: torch.Tensor, n_fine: int, u: Optional[torch.Tensor] = None):
-    """A7: t_coarse [n_coarse] or [R,n_coarse]; weights [R,n_coarse]; u None | [n_fine] | [R,n_fine]."""
+def sample_pdf(t_coarse: torch.Tensor, weights: torch.Tensor, n_fine: int, u: Optional[torch.Tensor] = None,
+               rng: Optional[Rng] = None):
+    """A7: t_coarse [n_coarse] or [R,n_coarse]; weights [R,n_coarse]; u None | [n_fine] | [R,n_fine]; rng (with u None):
+    the inverse-cdf draws are generated in the kernel."""
     lib = load()
     R, nc = weights.shape
     t_stride = 0 if t_coarse.dim() == 1 else nc
     u_stride = 0 if (u is None or u.dim() == 1) else n_fine
     out = torch.empty(R, nc + n_fine, dtype=torch.float32, device=weights.device)
     with _on(weights.device):
+        if rng is not None and u is None:
+            r = rng.struct()
+            _check(lib.aon_sample_pdf_rng(_ptr(t_coarse, "t_coarse"), t_stride, _ptr(weights, "weights"), C.byref(r),
+                                          R, nc, n_fine, _ptr(out), _stream()), "aon_sample_pdf_rng")
+            return out
         _check(lib.aon_sample_pdf(_ptr(t_coarse, "t_coarse"), t_stride, _ptr(weights, "weights"), _ptr(u, "u"), u_stride,
                                   R, nc, n_fine, _ptr(out), _stream()), "aon_sample_pdf")
     return out

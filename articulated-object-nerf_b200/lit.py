@@ -238,8 +238,9 @@ class GraphedStep:
     their execution; a replay costs microseconds of host time.  Shapes must not change between steps (the reference's
     fixed-size ray batches, model.py:421-428 / sapien_multi.py:235).  The batch is copied into static buffers; the learning
     rate / bias corrections reach the Adam kernel through a 7-float device buffer refreshed before every replay
-    (aon_adam_step_dev), because a graph bakes kernel arguments in.  torch's CUDA generator is graph-aware, so the stratified
-    and inverse-cdf draws differ from replay to replay as they must."""
+    (aon_adam_step_dev), because a graph bakes kernel arguments in.  The stratified and inverse-cdf draws are generated inside
+    the sampling kernels from a step counter in device memory that the captured step advances itself (lib.Rng), so they differ
+    from replay to replay as they must -- and are the same draws an eager step would have made."""
 
     RING = 64
 
@@ -259,8 +260,9 @@ class GraphedStep:
         # DRY RUN: warm-up steps on a side stream (allocator pools, lazily created handles, tensor-map cache) and the capture
         # itself must not count as training -- parameters, Adam moments, step counters and the generator state are restored
         # afterwards, so the first replay is the first real step on this batch
+        rng = system.model.rng(dev) if hasattr(system.model, "rng") else None        # in-kernel Philox step counter (device memory)
         saved = (opt.flat.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.steps, system.trainer.global_step,
-                 torch.cuda.get_rng_state(dev))
+                 torch.cuda.get_rng_state(dev), None if rng is None else rng.offset_dev.clone())
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -285,6 +287,8 @@ class GraphedStep:
                 opt.flat.copy_(saved[0]); opt.exp_avg.copy_(saved[1]); opt.exp_avg_sq.copy_(saved[2])
             opt.steps, system.trainer.global_step = saved[3], saved[4]
             torch.cuda.set_rng_state(saved[5], dev)
+            if rng is not None:
+                rng.offset_dev.copy_(saved[6])
             for p in opt.param_groups[0]["params"]:
                 torch.autograd.graph.increment_version(p)
             if self.graph is None:

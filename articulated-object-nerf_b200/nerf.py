@@ -260,16 +260,25 @@ class _LevelLoop(nn.Module):
         if R == 0:      # empty ray batch: nothing to launch (the C ABI rejects null pointers)
             e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
             return [(e(0, 3), e(0), e(0)), (e(0, 3), e(0), e(0))]
+        rng = None
         if randomized:
-            if t_rand is None:
-                t_rand = torch.rand(R, nc, device=dev)
-            if u is None:
-                u = torch.rand(R, self.num_fine_samples, device=dev)
-            t0 = L.sample_along_rays(near, far, nc, R, dev, t_rand=t_rand.contiguous())
+            # helper.py:126 / :227 draw with torch.rand; here the draws are generated INSIDE the sampling kernels (Philox,
+            # sampling.cuh) unless the caller injects t_rand / u tensors (tests): no [R,65] / [R,128] uniforms in HBM
+            if t_rand is None or u is None:
+                rng = self.rng(dev)
+            t0 = L.sample_along_rays(near, far, nc, R, dev, t_rand=None if t_rand is None else t_rand.contiguous(),
+                                     rng=rng if t_rand is None else None)
         if need_grad:
             if not randomized:
                 t0 = L.sample_along_rays(near, far, nc, R, dev)
-            return self._render_autograd(o, d, v, t0, u, white_bkgd, latents)
+            ret = self._render_autograd(o, d, v, t0, u, white_bkgd, latents, rng if u is None else None)
+            if rng is not None:
+                rng.advance()
+            return ret
+        if rng is not None:                 # randomized render without gradients (not a reference code path): the fused
+            if u is None:                   # kernel takes the inverse-cdf draws as a tensor
+                u = rng.uniform(1, R, self.num_fine_samples)
+            rng.advance()
         kind = self.coarse_mlp.KIND
         pc = self._cache["coarse"].get(self.coarse_mlp, self.precision)
         pf = self._cache["fine"].get(self.fine_mlp, self.precision)
@@ -284,7 +293,16 @@ class _LevelLoop(nn.Module):
                                      t_coarse=t0 if randomized else None, u=None if u is None else u.contiguous())
         return [(coarse[:, :3], coarse[:, 3], coarse[:, 4]), (fine[:, :3], fine[:, 3], fine[:, 4])]
 
-    def _render_autograd(self, o, d, v, t0, u, white_bkgd, latents):
+    def rng(self, device) -> "L.Rng":
+        """Philox state of the randomized sampling steps: seed = torch.initial_seed() + rank at first use (or ``rng_seed``)."""
+        r = getattr(self, "_rng", None)
+        if r is None or r.offset_dev.device != torch.device(device):
+            from . import dist as D
+            seed = getattr(self, "rng_seed", None)
+            r = self._rng = L.Rng((torch.initial_seed() + D.world()[0]) if seed is None else seed, device)
+        return r
+
+    def _render_autograd(self, o, d, v, t0, u, white_bkgd, latents, rng=None):
         R = o.shape[0]
         ret = []
         t_vals = t0 if t0.dim() == 2 else t0[None, :].expand(R, -1).contiguous()
@@ -293,7 +311,7 @@ class _LevelLoop(nn.Module):
         for level, mlp in enumerate((self.coarse_mlp, self.fine_mlp)):
             if level == 1:
                 t_vals = L.sample_pdf(t_vals, weights.detach().contiguous(), self.num_fine_samples,
-                                      u=None if u is None else u.contiguous())
+                                      u=None if u is None else u.contiguous(), rng=rng)
             samples = o[:, None, :] + t_vals[..., None] * d[:, None, :]
             tc = self.train_gemm in ("tc", "tc16")           # tcgen05 GEMMs: fp16 hi+lo planes ("tc") or the hi plane only ("tc16")
             if latents is None and tc:

@@ -97,6 +97,24 @@ int aon_raygen(int H, int W, float focal, const float* c2w_host, float* rays_o, 
 int aon_sample_along_rays(float near, float far, int n_points, const float* t_rand, int R,
                           float* t_vals, aon_stream_t stream);
 
+/* In-kernel random draws for the two randomized sampling steps of training (helper.py:126 `torch.rand(batch, num_samples+1)`,
+ * helper.py:227 `torch.rand(..., num_samples)`): Philox4x32-10 evaluated as a function of (seed, offset, stream, ray, column)
+ * inside the sampling kernels -- no [R,65] / [R,128] tensor of uniforms exists.  The effective step offset is
+ * offset + *offset_dev (offset_dev may be NULL); a training step captured in a CUDA graph keeps its step counter in device
+ * memory and bumps it with aon_rng_advance inside the graph.  The bit stream is this library's (oracle/philox.py restates
+ * it), not torch's: the reference draws from torch's global generator, whose stream depends on the launch shape.
+ * stream ids: 0 = stratified jitter, 1 = inverse-cdf draws.  aon_rng_uniform writes the draws [rows, cols] themselves
+ * (tests / debugging; the sampling kernels never materialise them). */
+typedef struct AonRng {
+  unsigned long long seed;
+  unsigned long long offset;
+  const unsigned long long* offset_dev;   /* device pointer or NULL */
+} AonRng;
+int aon_sample_along_rays_rng(float near, float far, int n_points, const AonRng* rng, int R,
+                              float* t_vals, aon_stream_t stream);
+int aon_rng_uniform(const AonRng* rng, int stream_id, int rows, int cols, float* out, aon_stream_t stream);
+int aon_rng_advance(unsigned long long* offset_dev, unsigned long long by, aon_stream_t stream);
+
 /* ---- workspace + per-call options ---------------------------------------------------------------------
  * aon_workspace_bytes: bytes of device scratch (256-byte aligned) that aon_render_level / aon_render_rays /
  * aon_render_image / aon_render_image_host need for up to R rays in `precision`; 0 for a bad precision.
@@ -140,6 +158,9 @@ int aon_render_level(int kind, int precision, const void* packed, const float* f
 int aon_sample_pdf(const float* t_coarse, long t_stride, const float* weights, const float* u,
                    long u_stride, int R, int n_coarse, int n_fine, float* t_fine,
                    aon_stream_t stream);
+/* the same with the inverse-cdf draws u [R,n_fine] generated in the kernel (AonRng above, stream 1) */
+int aon_sample_pdf_rng(const float* t_coarse, long t_stride, const float* weights, const AonRng* rng,
+                       int R, int n_coarse, int n_fine, float* t_fine, aon_stream_t stream);
 
 /* ---- A8/A11  the whole level loop of NeRF.forward in ONE kernel ---------------------------------------
  * Replaces NeRF.forward / NeRF_AE_Art.forward (model.py:147-199; model_autodecoder.py:278-337) and the

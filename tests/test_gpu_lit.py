@@ -57,11 +57,14 @@ def test_lit_eval_and_train(built_lib, exp):
     assert losses[-1] < losses[0], losses
 
 
+@pytest.mark.parametrize("randomized", [False, True])
 @pytest.mark.parametrize("exp", ["vanilla", "vanilla_autodecoder"])
-def test_graphed_step_equals_eager(built_lib, exp):
+def test_graphed_step_equals_eager(built_lib, exp, randomized):
     """lit.Trainer replays the training step as a CUDA graph (lit.GraphedStep: static batch buffers, Adam scalars through
-    device memory, dry-run capture).  With the random draws switched off the replayed steps must leave EXACTLY the parameters
-    the eager loop leaves: same kernels, deterministic reductions, same learning-rate schedule, capture trains nothing."""
+    device memory, dry-run capture).  The replayed steps must leave EXACTLY the parameters the eager loop leaves: same kernels,
+    deterministic reductions, same learning-rate schedule, capture trains nothing -- also with the randomized sampling on,
+    because the stratified / inverse-cdf draws are generated in the sampling kernels from a step counter in device memory
+    (lib.Rng) that eager and replayed steps advance alike."""
     from aon_b200 import lit
     dev = torch.device("cuda:0")
     rays = {k: v.to(dev) for k, v in O.sapien_rays(24, 32, seed=5).items()}
@@ -81,7 +84,8 @@ def test_graphed_step_equals_eager(built_lib, exp):
     for graph in (False, True):
         torch.manual_seed(0)
         s = lit.build_system(_hp(exp)).to(dev)
-        s.randomized = False
+        s.randomized = randomized
+        s.model.rng_seed = 7
         s.lr_delay_steps = 4                                 # the learning rate changes every step
         tr = lit.Trainer(max_steps=6, cuda_graph=graph)
         tr.fit(s, batches())

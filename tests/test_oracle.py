@@ -155,3 +155,24 @@ def test_training_gradients_golden(kind, golden_dir):
             ref = _t(g[key])
             got = p[key[5:]].grad
             assert (got - ref).abs().max() <= 1e-5 * ref.abs().max().clamp_min(1e-12), key
+
+
+def test_philox_known_answers():
+    """oracle/philox.py against the known-answer vectors of the Philox authors' Random123 distribution
+    (kat_vectors: philox4x32, 10 rounds) -- the generator csrc/sampling.cuh evaluates inside the sampling kernels."""
+    from oracle import philox as P
+
+    def run(ctr, key):
+        return [int(x) for x in P.philox4x32_10([np.uint32(v) for v in ctr], key)]
+
+    assert run([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert run([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert run([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    u = P.uniform(seed=7, offset=3, stream=1, rows=257, cols=128)
+    assert u.dtype == np.float32 and u.min() >= 0.0 and u.max() < 1.0
+    assert abs(float(u.mean()) - 0.5) < 0.01 and abs(float(u.var()) - 1.0 / 12.0) < 0.005
+    # streams, offsets and seeds are independent coordinates of the counter / key
+    assert not np.array_equal(u, P.uniform(7, 3, 0, 257, 128)) and not np.array_equal(u, P.uniform(7, 4, 1, 257, 128))
+    assert not np.array_equal(u, P.uniform(8, 3, 1, 257, 128))
+    # a draw is a function of (row, column) only: sub-blocks agree
+    assert np.array_equal(u[:33, :65], P.uniform(7, 3, 1, 33, 65))
