@@ -634,6 +634,52 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, long ld, int C, 
   }
 }
 
+// the same into the tile order of the fused training forward (render_tc.cu, TrainDump): packed row (tile rt * S + s, r) reads
+// source row (rt*128 + r) * S + s, or rt*128 + r when the source is per ray; rows of rays >= R are zero
+__global__ void pack_rows_tiled_kernel(const float* __restrict__ src, long ld, int C, int R, int S, int per_ray, long m_tiles, int c_pad,
+                                       float scale, uint4* __restrict__ hi, uint4* __restrict__ lo) {
+  const long total = m_tiles * (c_pad / 8) * 128;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int row = (int)(idx & 127);
+    const long rest = idx >> 7;
+    const int kg = (int)(rest % (c_pad / 8));
+    const long tile = rest / (c_pad / 8);
+    const long ray = (tile / S) * 128 + row;
+    const long m = per_ray ? ray : ray * S + (tile % S);
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = kg * 8 + j;
+      s[j] = (ray < R && c < C) ? src[m * ld + c] * scale : 0.f;
+    }
+    uint4 h;
+    h.x = pack_h2(s[0], s[1]); h.y = pack_h2(s[2], s[3]); h.z = pack_h2(s[4], s[5]); h.w = pack_h2(s[6], s[7]);
+    hi[idx] = h;
+    if (lo) {
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+      float l[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        l[2 * j] = s[2 * j] - __half2float(__ushort_as_half((unsigned short)(hw[j] & 0xffffu)));
+        l[2 * j + 1] = s[2 * j + 1] - __half2float(__ushort_as_half((unsigned short)(hw[j] >> 16)));
+      }
+      uint4 q;
+      q.x = pack_h2(l[0], l[1]); q.y = pack_h2(l[2], l[3]); q.z = pack_h2(l[4], l[5]); q.w = pack_h2(l[6], l[7]);
+      lo[idx] = q;
+    }
+  }
+}
+
+__global__ void unpack_rows_tiled_kernel(const float* __restrict__ src, long ld, int C, int R, int S, float* __restrict__ dst) {
+  const long total = (long)R * S * C;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const long m = idx / C;
+    const long ray = m / S, s = m % S;
+    dst[idx] = src[(((ray >> 7) * S + s) * 128 + (ray & 127)) * ld + c];
+  }
+}
+
 // nn.Linear weight W [out, in] fp32 -> PW(r_pad, k_pad) = [k_pad/8][r_pad][8] hi (+ lo) * scale;
 // transpose = 0: rows = out features, contraction = in features (forward); 1: rows = in, contraction = out (dgrad).
 __global__ void pack_linear_kernel(const float* __restrict__ W, int out_f, int in_f, int transpose, int r_pad, int k_pad, float scale,
@@ -836,6 +882,27 @@ extern "C" int aon_pack_rows(const float* src, long ld, int C, long M, int row_d
   const long blocks = (total + 255) / 256;
   pack_rows_kernel<<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, (cudaStream_t)stream>>>(src, ld, C, M, row_div, m_tiles, c_pad, scale,
                                                                                                    (uint4*)hi, (uint4*)lo);
+  AON_LAUNCH_CHECK();
+  return AON_OK;
+}
+
+extern "C" int aon_pack_rows_tiled(const float* src, long ld, int C, int R, int S, int per_ray, int c_pad, float scale, void* hi, void* lo,
+                                   aon_stream_t stream) {
+  AON_REQUIRE(src && hi && C >= 1 && R >= 1 && S >= 1 && c_pad >= C && c_pad % 8 == 0 && ld >= C, "aon_pack_rows_tiled: bad arguments");
+  const long m_tiles = (long)((R + 255) / 256) * 2 * S;
+  const long total = m_tiles * (c_pad / 8) * 128;
+  const long blocks = (total + 255) / 256;
+  pack_rows_tiled_kernel<<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, (cudaStream_t)stream>>>(src, ld, C, R, S, per_ray, m_tiles, c_pad,
+                                                                                                         scale, (uint4*)hi, (uint4*)lo);
+  AON_LAUNCH_CHECK();
+  return AON_OK;
+}
+
+extern "C" int aon_unpack_rows_tiled(const float* src, long ld, int C, int R, int S, float* dst, aon_stream_t stream) {
+  AON_REQUIRE(src && dst && C >= 1 && R >= 1 && S >= 1 && ld >= C, "aon_unpack_rows_tiled: bad arguments");
+  const long total = (long)R * S * C;
+  const long blocks = (total + 255) / 256;
+  unpack_rows_tiled_kernel<<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, (cudaStream_t)stream>>>(src, ld, C, R, S, dst);
   AON_LAUNCH_CHECK();
   return AON_OK;
 }

@@ -343,8 +343,23 @@ struct SmemPlan {
   static_assert(NSTAGE >= 3, "weight ring too small");
 };
 
+// Training forward (TRAIN instantiations): every unit's output -- the activation the backward GEMMs of csrc/gemm_tc.cu need as
+// wgrad operand and ReLU mask -- leaves the epilogue ONCE, as 16-byte rows of the packed plane layout of gemm_tc.cu
+// ([tile][feature / 8][128 rows][8] 16-bit, hi and lo plane), which is this kernel's shared-memory operand layout; the next
+// layer reads it from shared memory, never from HBM.  Row tile of (ray tile rt, sample s) = rt * S + s, row = ray % 128.
+struct TrainDump {
+  uint4* hi[MAX_UNITS];
+  uint4* lo[MAX_UNITS];
+  uint32_t* bits[MAX_UNITS];   // [tiles * 128][N / 32] ReLU masks (bit i of word c: feature 32 c + i > 0) or nullptr
+  uint4* e_hi;                 // encoding operand [tiles][8][128]
+  uint4* e_lo;
+  float4* raw;                 // [R * S] in ray-major order: (r, g, b) before the sigmoid, raw density
+  float* warped;               // auto-decoder: [tiles * 128][3] warped positions, tile order
+};
+
 struct TcParams {
   Program prog;
+  TrainDump dump;
   PackedLayout L;
   // per level: the fused image kernel walks level 0 (coarse) then level 1 (fine); a classic launch has level 0 only
   const char* packed[2];
@@ -537,7 +552,7 @@ __device__ __forceinline__ void load_ray(const TcParams& p, int row, float (&o)[
   }
 }
 
-template <int KIND, bool X3, bool BF16>
+template <int KIND, bool X3, bool BF16, bool TRAIN>
 __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_constant__ TcParams p) {
   using SP = SmemPlan<KIND, X3>;
   // no-swizzle operand layouts and bulk copies need 16-byte / 128-byte alignment only
@@ -892,6 +907,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           for (int k = 0; k < 3; ++k) x[k] = xw[128 * k + row];
         }
         encode_store<10, 64, X3, BF16>(sm + E_OFF, LO_E, row, x);
+        if (TRAIN) {   // this thread's row of the encoding operand (its own shared-memory writes) -> packed plane in HBM
+          const size_t tile = (size_t)blockIdx.x * SG + (sb + s);
+#pragma unroll
+          for (int kg = 0; kg < 8; ++kg) {
+            p.dump.e_hi[(tile * 8 + kg) * 128 + row] = *reinterpret_cast<const uint4*>(sm + E_OFF + kg * 2048 + row * 16);
+            if (X3) p.dump.e_lo[(tile * 8 + kg) * 128 + row] = *reinterpret_cast<const uint4*>(sm + E_OFF + LO_E + kg * 2048 + row * 16);
+          }
+        }
         publish(CH_E0);
         publish(CH_E0 + 1);
         if (tid == 256) mark(2, pl, 0, 1);
@@ -998,6 +1021,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }
+          if (TRAIN) {
+            const size_t tile = (size_t)blockIdx.x * SG + (sb + s);
+            const int nkg = u.n128 * 16;   // k-groups (8 features) of this unit's output plane
+            if (relu && p.dump.bits[ui] != nullptr) {
+              uint32_t bits = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) bits |= (uint32_t)(v[i] > 0.f) << i;
+              p.dump.bits[ui][(tile * 128 + row) * (size_t)(u.n128 * 4) + cc] = bits;
+            }
+            uint4* gh = p.dump.hi[ui] + (tile * nkg + cc * 4) * 128 + row;
+            uint4* gl = X3 ? p.dump.lo[ui] + (tile * nkg + cc * 4) * 128 + row : nullptr;
+#pragma unroll
+            for (int kg = 0; kg < 4; ++kg) {
+              uint4 hi, lo;
+              pack8<X3, BF16>(v + kg * 8, hi, lo);
+              gh[kg * 128] = hi;
+              if (X3) gl[kg * 128] = lo;
+            }
+          }
           if (epi == EPI_STORE_SIGMA) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -1054,13 +1096,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
           xw[row] = __fadd_rn(h0 + hb[0], __fadd_rn(ox, __fmul_rn(t_cur, dx)));
           xw[128 + row] = __fadd_rn(h1 + hb[1], __fadd_rn(oy, __fmul_rn(t_cur, dy)));
           xw[256 + row] = __fadd_rn(h2 + hb[2], __fadd_rn(oz, __fmul_rn(t_cur, dz)));
+          if (TRAIN) {
+            const size_t m = ((size_t)blockIdx.x * SG + (sb + s)) * 128 + row;
+            p.dump.warped[3 * m + 0] = xw[row]; p.dump.warped[3 * m + 1] = xw[128 + row]; p.dump.warped[3 * m + 2] = xw[256 + row];
+          }
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bar(BAR_XW));
         }
       }
 
       // ---- activations + alpha compositing of sample s (helper.py:157-195) ----
-      if (owner) {
+      if (TRAIN) {
+        // training forward: the raw network outputs leave the kernel; activations + compositing (and their adjoints) are
+        // aon_composite / aon_composite_backward on [R,S,4]
+        if (owner && valid) {
+          const float* hb = hw_rgb + 384;
+          p.dump.raw[ray * SG + sb + s] = make_float4(h0 + hb[0], h1 + hb[1], h2 + hb[2], sig + hw_sig[256]);
+        }
+      } else if (owner) {
         const float raw_sigma = sig + hw_sig[256];
         const float* hb = hw_rgb + 384;
         float rr = h0 + hb[0], gg = h1 + hb[1], bb = h2 + hb[2];
@@ -1096,7 +1149,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
       t_cur = t_next;
     }
 
-      if (valid && owner && p.n_seg == 1) {
+      if (!TRAIN && valid && owner && p.n_seg == 1) {
         if (isnan(cdepth)) cdepth = INFINITY;  // helper.py:179 nan_to_num(depth, nan=inf)
         else if (isinf(cdepth)) cdepth = cdepth > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
         if (p.white_bkgd) {
@@ -1178,10 +1231,10 @@ static int choose_segments(int pairs, int S, int pair_slots) {
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
-template <int KIND, bool X3, bool BF16>
+template <int KIND, bool X3, bool BF16, bool TRAIN = false>
 static int launch(const TcParams& p, int grid, int grid_y, cudaStream_t st) {
   using SP = SmemPlan<KIND, X3>;
-  auto kern = render_tc_kernel<KIND, X3, BF16>;
+  auto kern = render_tc_kernel<KIND, X3, BF16, TRAIN>;
   AON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1212,6 +1265,19 @@ static int launch_any(const TcParams& p, int kind, int precision, int grid, int 
       return van ? launch<AON_KIND_VANILLA, false, true>(p, grid, grid_y, st) : launch<AON_KIND_AUTODECODER, false, true>(p, grid, grid_y, st);
     default:
       set_error("bad precision %d", precision);
+      return AON_E_ARG;
+  }
+}
+
+static int launch_train(const TcParams& p, int kind, int precision, int grid, int grid_y, cudaStream_t st) {
+  const bool van = kind == AON_KIND_VANILLA;
+  switch (precision) {
+    case AON_PREC_TC_F16X3:
+      return van ? launch<AON_KIND_VANILLA, true, false, true>(p, grid, grid_y, st) : launch<AON_KIND_AUTODECODER, true, false, true>(p, grid, grid_y, st);
+    case AON_PREC_TC_F16:
+      return van ? launch<AON_KIND_VANILLA, false, false, true>(p, grid, grid_y, st) : launch<AON_KIND_AUTODECODER, false, false, true>(p, grid, grid_y, st);
+    default:
+      set_error("training forward: precision must be f16x3 or f16 (got %d)", precision);
       return AON_E_ARG;
   }
 }
@@ -1327,6 +1393,42 @@ int render_level_tc(int kind, int precision, const void* packed, const float* fo
   return render_range(p, kind, precision, R - R_main, n_tail, seg_buf, st);
 }
 
+// Training forward of ONE level over rays [0, R): the MLP chain of all R * S samples in one launch, every layer output written
+// once (TrainDump), raw outputs in ray-major order.  Sample segments spread a small ray batch over all SMs (no compositing
+// here, so segments need no scratch).  Row tiles: ((R + 255) / 256 * 2) * S.
+int forward_train_tc(int kind, int precision, const void* packed, const float* folded, const float* rays_o, const float* rays_d,
+                     const float* viewdirs, const float* t_vals, long t_stride, int R, int S, const TrainDump& dump, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  int rc = device_info(&dev, &sms);
+  if (rc != AON_OK) return rc;
+  TcParams p;
+  fill_common(p, kind, precision, nullptr);
+  p.dump = dump;
+  p.packed[0] = (const char*)packed;
+  p.folded[0] = folded;
+  p.S_level[0] = S;
+  p.n_levels = 1;
+  p.rays_o = rays_o; p.rays_d = rays_d; p.viewdirs = viewdirs;
+  p.t_vals = t_vals; p.t_stride = t_stride;
+  p.R = R;
+  const int pairs = (R + 255) / 256, slots = sms / 2;
+  // samples per CTA: as many segments as it takes to fill the pair slots (cost model of choose_segments)
+  int n_seg = 1;
+  {
+    long best = -1;
+    for (int n = 1; n <= S; ++n) {
+      const long waves = ((long)pairs * n + slots - 1) / slots;
+      const long cost = waves * ((S + n - 1) / n + 2);
+      if (best < 0 || cost < best) { best = cost; n_seg = n; }
+    }
+  }
+  p.n_seg = n_seg;
+  p.seg_len = (S + n_seg - 1) / n_seg;
+  n_seg = (S + p.seg_len - 1) / p.seg_len;     // no empty trailing segment
+  p.n_seg = n_seg;
+  return launch_train(p, kind, precision, pairs * 2, n_seg, st);
+}
+
 // The fused image kernel over rays [0, R): coarse level, in-kernel hierarchical sampling, fine level in ONE launch; no
 // per-sample tensor reaches HBM.  slots / slot_mask live in the caller's workspace (mask zeroed by the caller).
 int render_fused_tc(int kind, int precision, const void* packed_c, const void* packed_f, const float* folded_c,
@@ -1386,6 +1488,30 @@ extern "C" int aon_pack_weights_tc(int kind, int precision, const float* const* 
   else pack_stream_kernel<false, true><<<blocks, 256, 0, st>>>(P, src, out);
   AON_LAUNCH_CHECK();
   return pack_tail(kind, L, w, b, (char*)packed, st);
+}
+
+extern "C" int aon_train_tiles(int R, int S) { return (R <= 0 || S <= 0) ? 0 : ((R + 255) / 256) * 2 * S; }
+
+extern "C" int aon_forward_train(int kind, int precision, const void* packed, const float* folded, const float* rays_o,
+                                 const float* rays_d, const float* viewdirs, const float* t_vals, long t_stride, int R, int S,
+                                 const AonTrainDump* d, aon_stream_t stream) {
+  AON_REQUIRE(kind == AON_KIND_VANILLA || kind == AON_KIND_AUTODECODER, "bad kind %d", kind);
+  AON_REQUIRE(packed && rays_o && rays_d && viewdirs && t_vals && d, "aon_forward_train: null pointer");
+  AON_REQUIRE(kind == AON_KIND_VANILLA || (folded != nullptr && d->warped != nullptr),
+              "aon_forward_train: auto-decoder needs the folded biases of aon_fold_latents() and a warped-position buffer");
+  AON_REQUIRE(R >= 1 && S >= 1 && (t_stride == 0 || t_stride >= S), "aon_forward_train: bad sizes R=%d S=%d t_stride=%ld", R, S, t_stride);
+  AON_REQUIRE(((uintptr_t)packed & 255) == 0, "packed buffer must be 256-byte aligned");
+  const bool x3 = precision == AON_PREC_TC_F16X3;
+  AON_REQUIRE(d->raw && d->enc_hi && (!x3 || d->enc_lo), "aon_forward_train: raw / encoding buffers missing");
+  TrainDump td;
+  memset(&td, 0, sizeof(td));
+  const int ng = num_gemm(kind);
+  for (int i = 0; i < ng; ++i) {
+    AON_REQUIRE(d->act_hi[i] && (!x3 || d->act_lo[i]), "aon_forward_train: activation plane of unit %d missing", i);
+    td.hi[i] = (uint4*)d->act_hi[i]; td.lo[i] = (uint4*)d->act_lo[i]; td.bits[i] = (uint32_t*)d->relu_bits[i];
+  }
+  td.e_hi = (uint4*)d->enc_hi; td.e_lo = (uint4*)d->enc_lo; td.raw = (float4*)d->raw; td.warped = d->warped;
+  return forward_train_tc(kind, precision, packed, folded, rays_o, rays_d, viewdirs, t_vals, t_stride, R, S, td, (cudaStream_t)stream);
 }
 
 // Introspection for tools / tests (not part of the public ABI in include/aon.h): program size and shared-memory plan.

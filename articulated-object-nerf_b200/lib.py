@@ -56,6 +56,10 @@ SYMBOLS = {
     "aon_pack_linear": (_i, [_fp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "aon_wgrad_reduce": (_i, [_fp, _i, _i, _i, _f, _fp, _l, _i, _i, _i, _i, _vp]),
     "aon_colsum_packed": (_i, [_vp, _vp, _i, _i, _i, _fp, _vp]),
+    "aon_train_tiles": (_i, [_i, _i]),
+    "aon_forward_train": (_i, [_i, _i, _vp, _fp, _fp, _fp, _fp, _fp, _l, _i, _i, _vp, _vp]),
+    "aon_pack_rows_tiled": (_i, [_fp, _l, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "aon_unpack_rows_tiled": (_i, [_fp, _l, _i, _i, _i, _fp, _vp]),
     "aon_launch_count": (_l, [_i]),
 }
 
@@ -593,6 +597,71 @@ def gemm_tn(A: PK, a_off: int, a_tiles: int, B: PK, b_off: int, N: int, splits: 
     with _on(A.hi.device):
         _check(lib.aon_gemm_tc(C.byref(g), _stream()), "aon_gemm_tc(TN)")
     return part
+
+
+def pack_rows_tiled(src: torch.Tensor, R: int, S: int, c_pad: int, scale: float, per_ray: bool = False, x3: bool = True) -> PK:
+    """src fp32 [R*S, C] (or [R, C] with per_ray) -> PK in the tile order of forward_train (tile rt*S + s, row = ray % 128);
+    rows of rays >= R are zero."""
+    lib = load()
+    if not (src.is_cuda and src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1):
+        raise AonError("pack_rows_tiled: src must be a CUDA float32 [rows, C] tensor with contiguous rows")
+    if src.shape[0] != (R if per_ray else R * S):
+        raise AonError("pack_rows_tiled: src has %d rows, expected %d" % (src.shape[0], R if per_ray else R * S))
+    out = PK(lib.aon_train_tiles(R, S), c_pad, src.device, x3)
+    with _on(src.device):
+        _check(lib.aon_pack_rows_tiled(src.data_ptr(), src.stride(0), src.shape[1], R, S, int(per_ray), c_pad, float(scale),
+                                       out.hi.data_ptr(), _p(out.lo), _stream()), "aon_pack_rows_tiled")
+    return out
+
+
+def unpack_rows_tiled(src: torch.Tensor, R: int, S: int) -> torch.Tensor:
+    """fp32 [tiles*128, C] in tile order -> [R*S, C] ray-major."""
+    lib = load()
+    out = torch.empty(R * S, src.shape[1], dtype=torch.float32, device=src.device)
+    with _on(src.device):
+        _check(lib.aon_unpack_rows_tiled(_ptr(src, "src"), src.stride(0), src.shape[1], R, S, _ptr(out), _stream()), "aon_unpack_rows_tiled")
+    return out
+
+
+class AonTrainDump(C.Structure):
+    """Mirror of `struct AonTrainDump` in include/aon.h."""
+    _fields_ = [("act_hi", _vp * 28), ("act_lo", _vp * 28), ("relu_bits", _vp * 28), ("enc_hi", _vp), ("enc_lo", _vp),
+                ("raw", _vp), ("warped", _vp)]
+
+
+def forward_train(kind: int, precision: int, packed: torch.Tensor, folded: Optional[torch.Tensor], rays_o, rays_d, viewdirs,
+                  t_vals: torch.Tensor, S: int):
+    """The forward chain of one level in ONE launch of the fused kernel (aon_forward_train): returns (acts, enc, raw, warped)
+    -- acts[i] = PK plane of GEMM unit i's output (+ .bits for the ReLU layers), enc = PK(tiles, 64) encoding operand,
+    raw [R*S,4] ray-major, warped [tiles*128,3] (auto-decoder) or None."""
+    lib = load()
+    R, dev = rays_o.shape[0], rays_o.device
+    x3 = precision == PREC_TC_F16X3
+    tiles = lib.aon_train_tiles(R, S)
+    d = AonTrainDump()
+    acts = []
+    for i, (n_out, relu) in enumerate(UNIT_OUT[kind]):
+        pk = PK(tiles, n_out, dev, x3)
+        if relu:
+            pk.bits = torch.empty(tiles * 128, n_out // 32, dtype=torch.int32, device=dev)
+            d.relu_bits[i] = pk.bits.data_ptr()
+        d.act_hi[i], d.act_lo[i] = pk.hi.data_ptr(), _p(pk.lo)
+        acts.append(pk)
+    enc = PK(tiles, 64, dev, x3)
+    raw = torch.empty(R * S, 4, dtype=torch.float32, device=dev)
+    warped = torch.empty(tiles * 128, 3, dtype=torch.float32, device=dev) if kind == KIND_AUTODECODER else None
+    d.enc_hi, d.enc_lo, d.raw, d.warped = enc.hi.data_ptr(), _p(enc.lo), raw.data_ptr(), _p(warped)
+    t_stride = 0 if t_vals.dim() == 1 else t_vals.stride(0)
+    with _on(dev):
+        _check(lib.aon_forward_train(kind, precision, packed.data_ptr(), _ptr(folded, "folded"), _ptr(rays_o, "rays_o"),
+                                     _ptr(rays_d, "rays_d"), _ptr(viewdirs, "viewdirs"), _ptr(t_vals, "t_vals"), t_stride, R, S,
+                                     C.byref(d), _stream()), "aon_forward_train")
+    return acts, enc, raw, warped
+
+
+# (out features, relu) of every GEMM unit of the fused kernel, in unit order (csrc/aon_spec.h V_GEMM / A_GEMM)
+UNIT_OUT = {KIND_VANILLA: [(256, True)] * 8 + [(256, False), (128, True)],
+            KIND_AUTODECODER: [(128, True)] * 4 + [(256, True)] * 8 + [(256, False)] + [(128, True)] * 4}
 
 
 def wgrad_reduce(partial: torch.Tensor, scale: float, dst: torch.Tensor, col_off: int, rows_valid: int, cols_valid: int,

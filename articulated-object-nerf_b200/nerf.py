@@ -251,6 +251,9 @@ class _LevelLoop(nn.Module):
         # training_step contractions: "tc" = hand-written tcgen05 GEMMs on fp16 hi+lo operand planes (train_tc.py; fp32-grade
         # gradients), "tc16" = the same GEMMs on single fp16 planes (fast mode, ~1e-3 gradient noise), "torch" = library GEMMs
         self.train_gemm = os.environ.get("AON_TRAIN_GEMM", "tc")
+        # training forward of a level: "fused" = the whole MLP chain in one launch of the fused render kernel, every layer
+        # output written to HBM once (aon_forward_train); "layers" = one tcgen05 GEMM launch per nn.Linear
+        self.train_fwd = os.environ.get("AON_TRAIN_FWD", "fused")
 
     def _render(self, rays, randomized, white_bkgd, near, far, latents=None, t_rand=None, u=None):
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
@@ -312,8 +315,13 @@ class _LevelLoop(nn.Module):
             if level == 1:
                 t_vals = L.sample_pdf(t_vals, weights.detach().contiguous(), self.num_fine_samples,
                                       u=None if u is None else u.contiguous(), rng=rng)
-            samples = o[:, None, :] + t_vals[..., None] * d[:, None, :]
             tc = self.train_gemm in ("tc", "tc16")           # tcgen05 GEMMs: fp16 hi+lo planes ("tc") or the hi plane only ("tc16")
+            if latents is None and tc and self.train_fwd == "fused":
+                raw_rgb, raw_sigma = train_tc.vanilla_fused(o, d, v, t_vals, view_enc, mlp, x3=self.train_gemm == "tc")
+                comp, acc, weights, depth = composite_cuda(raw_rgb, raw_sigma, t_vals, d, white_bkgd, 0)
+                ret.append((comp, acc, depth))
+                continue
+            samples = o[:, None, :] + t_vals[..., None] * d[:, None, :]
             if latents is None and tc:
                 raw_rgb, raw_sigma = train_tc.vanilla_mlp(pos_enc_cuda(samples, 0, 10), view_enc, samples.shape[1], mlp,
                                                           x3=self.train_gemm == "tc")

@@ -119,67 +119,118 @@ class _VanillaMLPFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_raw):
-        global _X3
-        _X3 = ctx.x3
-        if ctx.pk is None:
-            raise L.AonError("the tcgen05 training path frees its saved operand planes in backward(): a second backward through the "
-                             "same graph (retain_graph) is not supported -- re-run the forward, or set train_gemm = 'torch'")
-        E, V, h, bott, hv = ctx.pk
-        W = ctx.W
-        M, tiles, S = ctx.dims
-        dev = g_raw.device
-        R = max(1, M // S)
-        SG = float(2 ** int(math.floor(math.log2(R))))
-        g_raw = g_raw.contiguous()
-        Gr = _pack_rows(g_raw, M, tiles, 16, SG)                       # columns 0-2 (+ sigma in column 3, unused here: zero weight rows)
-        Gs = _pack_rows(g_raw[:, 3:], M, tiles, 16, SG)                 # sigma gradient alone (C = 1)
-        inv_w = 1.0 / (SG * SA)
-        gW = [torch.empty_like(w) for w in W]           # every entry is written by a wgrad_reduce launch
-        gB = [None] * 12
-        gB[11] = g_raw[:, :3].sum(0)
-        gB[10] = g_raw[:, 3:].sum(0)
+        return (None, None, None) + _vanilla_backward(ctx, g_raw, None)
 
-        # rgb_layer: the packed gradient has 4 live columns (r, g, b, sigma); W_r^T padded with zero rows ignores sigma
-        _wgrad_head(hv, 128, Gr, 3, gW[11], inv_w)
-        WrT = _pack_linear(W[11], True, 128, 16, SW)
-        d_hv = _PK(tiles, 128, dev)
-        cs = _gemm_nt([(Gr, 0, 16, WrT, 0, 0)], 128, tiles, dev, epi=L.EPI_MASK, mask=(hv, 0), inv_scale=1.0 / SW, out=d_hv, colsum=True)
-        # views_linear.0 : inputs [bottleneck(256), view enc(27)]
-        _wgrad(d_hv, 128, bott, 0, 256, 256, gW[8], 0, inv_w)
-        _wgrad(d_hv, 128, V, 0, 32, 27, gW[8], 256, inv_w)
-        gB[8] = cs.sum(0) / SG
-        WvT = _pack_linear(W[8], True, 288, 128, SW)
-        d_bott = _PK(tiles, 256, dev)
-        cs = _gemm_nt([(d_hv, 0, 128, WvT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / SW, out=d_bott, colsum=True)
-        # bottleneck_layer and density_layer both read the last trunk activation h[7]
-        _wgrad(d_bott, 256, h[7], 0, 256, 256, gW[9], 0, inv_w)
-        gB[9] = cs.sum(0) / SG
-        _wgrad_head(h[7], 256, Gs, 1, gW[10], inv_w)
-        WbT = _pack_linear(W[9], True, 256, 256, SW)
-        WdT = _pack_linear(W[10], True, 256, 16, SW)
-        d = _PK(tiles, 256, dev)
-        cs = _gemm_nt([(d_bott, 0, 256, WbT, 0, 0), (Gs, 0, 16, WdT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[7], 0),
-                       inv_scale=1.0 / SW, out=d, colsum=True)
-        # trunk, last layer first: pts_linears.i maps x_i -> h[i], x_0 = E, x_i = h[i-1] (+ E for i = 5)
-        for i in range(7, -1, -1):
-            x = E if i == 0 else h[i - 1]
-            kin = 64 if i == 0 else 256
-            _wgrad(d, 256, x, 0, kin, 63 if i == 0 else 256, gW[i], 0, inv_w)
-            if i == 5:
-                _wgrad(d, 256, E, 0, 64, 63, gW[5], 256, inv_w)
-            gB[i] = cs.sum(0) / SG                           # column sums of d, produced by the GEMM that wrote d
-            if i == 0:
-                break
-            WT = _pack_linear(W[i], True, 320 if i == 5 else 256, 256, SW)
-            nd = _PK(tiles, 256, dev)
-            cs = _gemm_nt([(d, 0, 256, WT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[i - 1], 0), inv_scale=1.0 / SW, out=nd,
-                           colsum=True)
-            d = nd
-        ctx.pk = None
-        out = [None, None, None]
-        for w, b in zip(gW, gB):
-            out += [w, b]
-        return tuple(out)
+
+def _pack_grad(src: torch.Tensor, M: int, tiles: int, c_pad: int, scale: float, tiled) -> L.PK:
+    """gradient rows [M, C] (ray-major) -> packed plane: plain row order, or the tile order of the fused forward (tiled = (R, S))"""
+    if tiled is None:
+        return _pack_rows(src, M, tiles, c_pad, scale)
+    return L.pack_rows_tiled(src, tiled[0], tiled[1], c_pad, scale, x3=_X3)
+
+
+def _vanilla_backward(ctx, g_raw, tiled):
+    """dgrad chain + wgrads + bias gradients of NeRFMLP from the saved planes; returns the 24 parameter gradients."""
+    global _X3
+    _X3 = ctx.x3
+    if ctx.pk is None:
+        raise L.AonError("the tcgen05 training path frees its saved operand planes in backward(): a second backward through the "
+                         "same graph (retain_graph) is not supported -- re-run the forward, or set train_gemm = 'torch'")
+    E, V, h, bott, hv = ctx.pk
+    W = ctx.W
+    M, tiles, S = ctx.dims
+    dev = g_raw.device
+    R = max(1, M // S)
+    SG = float(2 ** int(math.floor(math.log2(R))))
+    g_raw = g_raw.contiguous()
+    Gr = _pack_grad(g_raw, M, tiles, 16, SG, tiled)                 # columns 0-2 (+ sigma in column 3, unused here: zero weight rows)
+    Gs = _pack_grad(g_raw[:, 3:], M, tiles, 16, SG, tiled)           # sigma gradient alone (C = 1)
+    inv_w = 1.0 / (SG * SA)
+    gW = [torch.empty_like(w) for w in W]           # every entry is written by a wgrad_reduce launch
+    gB = [None] * 12
+    gB[11] = g_raw[:, :3].sum(0)
+    gB[10] = g_raw[:, 3:].sum(0)
+
+    # rgb_layer: the packed gradient has 4 live columns (r, g, b, sigma); W_r^T padded with zero rows ignores sigma
+    _wgrad_head(hv, 128, Gr, 3, gW[11], inv_w)
+    WrT = _pack_linear(W[11], True, 128, 16, SW)
+    d_hv = _PK(tiles, 128, dev)
+    cs = _gemm_nt([(Gr, 0, 16, WrT, 0, 0)], 128, tiles, dev, epi=L.EPI_MASK, mask=(hv, 0), inv_scale=1.0 / SW, out=d_hv, colsum=True)
+    # views_linear.0 : inputs [bottleneck(256), view enc(27)]
+    _wgrad(d_hv, 128, bott, 0, 256, 256, gW[8], 0, inv_w)
+    _wgrad(d_hv, 128, V, 0, 32, 27, gW[8], 256, inv_w)
+    gB[8] = cs.sum(0) / SG
+    WvT = _pack_linear(W[8], True, 288, 128, SW)
+    d_bott = _PK(tiles, 256, dev)
+    cs = _gemm_nt([(d_hv, 0, 128, WvT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / SW, out=d_bott, colsum=True)
+    # bottleneck_layer and density_layer both read the last trunk activation h[7]
+    _wgrad(d_bott, 256, h[7], 0, 256, 256, gW[9], 0, inv_w)
+    gB[9] = cs.sum(0) / SG
+    _wgrad_head(h[7], 256, Gs, 1, gW[10], inv_w)
+    WbT = _pack_linear(W[9], True, 256, 256, SW)
+    WdT = _pack_linear(W[10], True, 256, 16, SW)
+    d = _PK(tiles, 256, dev)
+    cs = _gemm_nt([(d_bott, 0, 256, WbT, 0, 0), (Gs, 0, 16, WdT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[7], 0),
+                   inv_scale=1.0 / SW, out=d, colsum=True)
+    # trunk, last layer first: pts_linears.i maps x_i -> h[i], x_0 = E, x_i = h[i-1] (+ E for i = 5)
+    for i in range(7, -1, -1):
+        x = E if i == 0 else h[i - 1]
+        kin = 64 if i == 0 else 256
+        _wgrad(d, 256, x, 0, kin, 63 if i == 0 else 256, gW[i], 0, inv_w)
+        if i == 5:
+            _wgrad(d, 256, E, 0, 64, 63, gW[5], 256, inv_w)
+        gB[i] = cs.sum(0) / SG                           # column sums of d, produced by the GEMM that wrote d
+        if i == 0:
+            break
+        WT = _pack_linear(W[i], True, 320 if i == 5 else 256, 256, SW)
+        nd = _PK(tiles, 256, dev)
+        cs = _gemm_nt([(d, 0, 256, WT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[i - 1], 0), inv_scale=1.0 / SW, out=nd,
+                       colsum=True)
+        d = nd
+    ctx.pk = None
+    out = []
+    for w, b in zip(gW, gB):
+        out += [w, b]
+    return tuple(out)
+
+
+class _VanillaFusedFn(torch.autograd.Function):
+    """(rays_o [R,3], rays_d [R,3], viewdirs [R,3], t_vals [R,S], view_enc [R,27], precision, w0, b0, ...) -> raw [R*S,4]:
+    cast_rays + pos_enc + the whole NeRFMLP forward chain of the level in ONE launch of the fused render kernel
+    (aon_forward_train, SURVEY.md 8f F1 stage 3): activations move from layer to layer through shared memory / TMEM and each
+    layer output is written to HBM once, as the packed planes the backward GEMMs read.  The backward is _vanilla_backward on
+    those planes (tile order of the fused kernel)."""
+
+    @staticmethod
+    def forward(ctx, o, d, v, t_vals, view_enc, precision, *params):
+        ctx.x3 = _X3
+        R, S = t_vals.shape
+        W = [p.detach().contiguous() for p in params[0::2]]
+        B = [p.detach().contiguous() for p in params[1::2]]
+        packed = L.pack_weights(L.KIND_VANILLA, precision, W, B)
+        acts, enc, raw, _ = L.forward_train(L.KIND_VANILLA, precision, packed, None, o, d, v, t_vals.contiguous(), S)
+        V = L.pack_rows_tiled(view_enc.detach().contiguous(), R, S, 32, SA, per_ray=True, x3=_X3)
+        ctx.pk = (enc, V, acts[0:8], acts[8], acts[9])
+        ctx.W = W
+        ctx.dims = (R * S, enc.m_tiles, S)
+        ctx.tiled = (R, S)
+        return raw
+
+    @staticmethod
+    def backward(ctx, g_raw):
+        return (None,) * 6 + _vanilla_backward(ctx, g_raw, ctx.tiled)
+
+
+def vanilla_fused(o, d, v, t_vals, view_enc, mlp, x3: bool = True) -> tuple:
+    """rays [R,3] x 3, t_vals [R,S], view_enc [R,27] -> (raw_rgb [R,S,3], raw_sigma [R,S,1]) through the fused forward chain."""
+    global _X3
+    _X3 = bool(x3)
+    params = []
+    for lin in mlp.linears():
+        params += [lin.weight, lin.bias]
+    R, S = t_vals.shape
+    raw = _VanillaFusedFn.apply(o, d, v, t_vals, view_enc, L.PREC_TC_F16X3 if x3 else L.PREC_TC_F16, *params)
+    return raw[:, :3].reshape(R, S, 3), raw[:, 3:].reshape(R, S, 1)
 
 
 def _fold(b: torch.Tensor, W: torch.Tensor, parts) -> torch.Tensor:

@@ -242,6 +242,39 @@ int aon_adam_scalars(double lr, double beta1, double beta2, double eps, long ste
 int aon_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n,
                       const float* scalars7_dev, aon_stream_t stream);
 
+/* ---- training path, stage 3: the forward chain of one level in ONE launch ---------------------------------------------
+ * Replaces, for training, cast_rays + pos_enc + NeRFMLP.forward of all R x S samples of a level (helper.py:25-26,136-140;
+ * model.py:95-120; model_autodecoder.py:171-239) -- the same fused kernel as aon_render_level, in a mode that keeps each
+ * layer's activations in shared memory / TMEM for the next layer and writes every layer output to HBM exactly ONCE, in the
+ * packed plane layout the backward GEMMs of aon_gemm_tc read ([tile][feature/8][128][8] 16-bit hi (+ lo) planes scaled by 8,
+ * plus a ReLU bit plane [rows][N/32]); no layer re-reads its input from HBM.  precision: AON_PREC_TC_F16X3 (hi + lo planes)
+ * or AON_PREC_TC_F16 (hi only).  Row tile of (ray tile rt, sample s) = rt * S + s, row within the tile = ray % 128;
+ * aon_train_tiles(R, S) = number of 128-row tiles = 2 * ceil(R / 256) * S (rows of rays >= R hold the last ray's values; the
+ * backward must feed them zero gradients: aon_pack_rows_tiled does).  act_* / relu_bits are indexed by GEMM unit (vanilla:
+ * pts_linears.0-7, bottleneck_layer, views_linear.0; auto-decoder: deformations_linear.0-3, pts_linears.0-7,
+ * bottleneck_layer, views_linear.0-3); relu_bits entries may be NULL.  raw: [R*S,4] ray-major (rgb before the sigmoid, raw
+ * density); warped (auto-decoder): [tiles*128,3] warped sample positions in tile order. */
+typedef struct AonTrainDump {
+  void* act_hi[28];
+  void* act_lo[28];
+  void* relu_bits[28];
+  void* enc_hi;
+  void* enc_lo;
+  float* raw;
+  float* warped;
+} AonTrainDump;
+int aon_train_tiles(int R, int S);
+int aon_forward_train(int kind, int precision, const void* packed, const float* folded, const float* rays_o,
+                      const float* rays_d, const float* viewdirs, const float* t_vals, long t_stride, int R, int S,
+                      const AonTrainDump* dump, aon_stream_t stream);
+/* fp32 -> packed planes in the tile order of aon_forward_train: packed row (tile rt * S + s, r) reads source row
+ * (rt*128 + r) * S + s (per_ray = 0: src is [R*S, C]) or rt*128 + r (per_ray = 1: src is [R, C], replicated over the
+ * samples); rows of rays >= R and columns >= C are zero. */
+int aon_pack_rows_tiled(const float* src, long ld, int C, int R, int S, int per_ray, int c_pad, float scale,
+                        void* hi, void* lo, aon_stream_t stream);
+/* the inverse for fp32 matrices: dst[(ray * S + s), 0:C] = src[(tile, r), 0:C] for ray < R (src in tile order, row stride ld) */
+int aon_unpack_rows_tiled(const float* src, long ld, int C, int R, int S, float* dst, aon_stream_t stream);
+
 /* ---- training path, stage 2: tcgen05 GEMMs for the MLP's forward / dgrad / wgrad (csrc/gemm_tc.cu) ------------
  * Replaces the nn.Linear contractions of NeRFMLP.forward (model.py:99-118) and their autograd adjoints in
  * training_step (model.py:256-282).  Operands are 16-bit hi (+ lo) planes in two packed layouts:

@@ -383,3 +383,72 @@ def test_autodecoder_mlp_tc_matches_autograd(built_lib):
         assert _rel(got[n], p.grad, floor=1e-12) < tol, (n, _rel(got[n], p.grad, floor=1e-12), tol)
     for k in lat:
         assert _rel(lat[k].grad, lat64[k].grad, floor=1e-12) < tol, (k, _rel(lat[k].grad, lat64[k].grad, floor=1e-12), tol)
+
+
+@pytest.mark.parametrize("gemm", ["tc", "tc16"])
+@pytest.mark.parametrize("R,S", [(96, 65), (300, 193)])
+def test_fused_training_forward_matches_autograd(built_lib, R, S, gemm):
+    """train_tc.vanilla_fused (aon_forward_train: cast_rays + pos_enc + the whole MLP chain of a level in ONE launch of the
+    fused render kernel, each layer output written once, tile order rt * S + s; backward = the tcgen05 dgrad / wgrad GEMMs on
+    those planes) against fp64 torch autograd of NeRFMLP.forward (model.py:95-120) on the same rays and sample positions.
+    R = 96 leaves the pair's second CTA without a valid ray, R = 300 ends in a ragged tile: the padded rows must contribute
+    nothing.  A pre-activation within rounding of zero takes either side of the ReLU in any finite-precision evaluation, and
+    ONE such sample moves a weight-gradient entry by ~1/sqrt(M) of itself (5e-3 here): the fp64 reference therefore applies
+    the ReLU masks the kernel wrote (its bit planes, read back through aon_unpack_rows_tiled), which makes the comparison
+    flip-free and strict -- "tc": raw outputs 1e-5, every gradient 2e-5 of its largest entry; "tc16" (single fp16 planes):
+    raw 5e-3, every gradient's cosine with the fp64 one > 0.995."""
+    from aon_b200 import nerf, train_tc, lib as L
+    sd = O.make_state_dict("vanilla", 0, sharp=False)
+    rays = {k: v[:R].contiguous().to(DEV) for k, v in O.sapien_rays(20, 24, seed=4).items()}
+    o, d, v = rays["rays_o"], rays["rays_d"], rays["viewdirs"]
+    g = torch.Generator().manual_seed(2)
+    t_vals = (2.0 + 4.0 * torch.rand(R, S, generator=g)).sort(-1).values.to(DEV)
+    g_up = (torch.randn(R * S, 4, generator=g) / R).to(DEV)        # O(1 / rays) like a mean-over-rays loss (train_tc.py scaling)
+    view_enc = nerf.pos_enc_cuda(v, 0, 4)
+    samples = o[:, None, :] + t_vals[..., None] * d[:, None, :]
+    enc = nerf.pos_enc_cuda(samples, 0, 10)
+    mlp = _make_net(nerf, "vanilla", sd, torch.device(DEV)).train().fine_mlp
+    rgb, sig = train_tc.vanilla_fused(o, d, v, t_vals, view_enc, mlp, x3=gemm == "tc")
+    raw = torch.cat([rgb, sig], -1).reshape(R * S, 4)
+    raw.backward(g_up)
+    got = {n: p.grad.clone() for n, p in mlp.named_parameters()}
+    # the kernel's planes: encoding operand and ReLU masks, back in ray-major order
+    lins = mlp.linears()
+    prec = L.PREC_TC_F16X3 if gemm == "tc" else L.PREC_TC_F16
+    packed = L.pack_weights(L.KIND_VANILLA, prec, [l.weight.detach() for l in lins], [l.bias.detach() for l in lins])
+    acts, enc_pk, raw_k, _ = L.forward_train(L.KIND_VANILLA, prec, packed, None, o, d, v, t_vals, S)
+    assert torch.equal(raw_k, raw.detach())                                      # deterministic
+    untile = lambda x: L.unpack_rows_tiled(x.contiguous(), R, S)
+    e_k = untile(enc_pk.to_dense())[:, :63] / 8.0
+    assert (e_k - enc.reshape(R * S, 63)).abs().max().item() < (2e-6 if gemm == "tc" else 2e-3)
+    masks = {}
+    for i, a in enumerate(acts):
+        if a.bits is not None:
+            b = torch.stack([((a.bits >> k) & 1) for k in range(32)], -1).reshape(a.bits.shape[0], -1).float()
+            masks[i] = untile(b).double().cpu()
+    P = {n: p.detach().double().cpu().requires_grad_(True) for n, p in mlp.named_parameters()}
+    E64, V64 = enc.reshape(R * S, 63).double().cpu(), view_enc.double().cpu().repeat_interleave(S, 0)
+    x = E64
+    for i in range(8):                                                            # model.py:99-110, ReLU = the kernel's mask
+        inp = x if i != 5 else torch.cat([x, E64], -1)
+        x = (inp @ P["pts_linears.%d.weight" % i].t() + P["pts_linears.%d.bias" % i]) * masks[i]
+    sigma = x @ P["density_layer.weight"].t() + P["density_layer.bias"]
+    bott = x @ P["bottleneck_layer.weight"].t() + P["bottleneck_layer.bias"]
+    hv = (torch.cat([bott, V64], -1) @ P["views_linear.0.weight"].t() + P["views_linear.0.bias"]) * masks[9]
+    rgb64 = hv @ P["rgb_layer.weight"].t() + P["rgb_layer.bias"]
+    raw64 = torch.cat([rgb64, sigma], -1)
+    raw64.backward(g_up.double().cpu())
+    if gemm == "tc":
+        assert _rel(raw, raw64) < 1e-5, _rel(raw, raw64)
+        worst = max(_rel(got[n], P[n].grad, floor=1e-12) for n in P)
+        print("fused forward R=%d S=%d: raw %.2e, worst gradient %.2e of its largest entry" % (R, S, _rel(raw, raw64), worst))
+        for n in P:
+            assert _rel(got[n], P[n].grad, floor=1e-12) < 2e-5, (n, _rel(got[n], P[n].grad, floor=1e-12))
+    else:
+        assert _rel(raw, raw64) < 5e-3
+        for n in P:
+            gf, r = got[n].double().cpu().flatten(), P[n].grad.flatten()
+            assert torch.isfinite(gf).all(), n
+            if r.norm() > 1e-12:
+                cos = (torch.dot(gf, r) / (gf.norm() * r.norm())).item()
+                assert cos > 0.995, (n, cos)
