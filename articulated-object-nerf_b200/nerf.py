@@ -316,9 +316,12 @@ class _LevelLoop(nn.Module):
                 t_vals = L.sample_pdf(t_vals, weights.detach().contiguous(), self.num_fine_samples,
                                       u=None if u is None else u.contiguous(), rng=rng)
             tc = self.train_gemm in ("tc", "tc16")           # tcgen05 GEMMs: fp16 hi+lo planes ("tc") or the hi plane only ("tc16")
-            if latents is None and tc and self.train_fwd == "fused":
-                raw_rgb, raw_sigma = train_tc.vanilla_fused(o, d, v, t_vals, view_enc, mlp, x3=self.train_gemm == "tc")
-                comp, acc, weights, depth = composite_cuda(raw_rgb, raw_sigma, t_vals, d, white_bkgd, 0)
+            if tc and self.train_fwd == "fused":
+                if latents is None:
+                    raw_rgb, raw_sigma = train_tc.vanilla_fused(o, d, v, t_vals, view_enc, mlp, x3=self.train_gemm == "tc")
+                else:
+                    raw_rgb, raw_sigma = train_tc.autodecoder_fused(o, d, v, t_vals, view_enc, latents, mlp, x3=self.train_gemm == "tc")
+                comp, acc, weights, depth = composite_cuda(raw_rgb, raw_sigma, t_vals, d, white_bkgd, 0 if latents is None else 1)
                 ret.append((comp, acc, depth))
                 continue
             samples = o[:, None, :] + t_vals[..., None] * d[:, None, :]

@@ -301,92 +301,142 @@ class _AutoDecoderMLPFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_raw):
-        global _X3
-        _X3 = ctx.x3
-        if ctx.pk is None:
-            raise L.AonError("the tcgen05 training path frees its saved operand planes in backward(): a second backward through the "
-                             "same graph (retain_graph) is not supported -- re-run the forward, or set train_gemm = 'torch'")
-        P, hd, warped, E, V, h, bott, hv = ctx.pk
-        W, (s_, c_, a_), (M, tiles, S) = ctx.W, ctx.codes, ctx.dims
-        dev = g_raw.device
-        SG = float(2 ** int(math.floor(math.log2(max(1, M // S)))))
-        inv_w = 1.0 / (SG * SA)
-        g_raw = g_raw.contiguous()
-        gW = [torch.empty_like(w) for w in W]
-        gB = [None] * 20
-        g_s, g_c, g_a = torch.zeros_like(s_), torch.zeros_like(c_), torch.zeros_like(a_)
+        return (None, None, None) + _autodecoder_backward(ctx, g_raw, None)
 
-        def dgrad(segs, n, mask, rows_pad, k_pad):
-            """segs: [(dY, kext, weight index, first row of W^T)] -> (PK(tiles, n) masked by `mask`, its column sums / SG)."""
-            out = _PK(tiles, n, dev)
-            gs = [(dY, 0, k, _pack_linear(W[wi], True, rows_pad[j], k_pad[j], SW), 0, r0) for j, (dY, k, wi, r0) in enumerate(segs)]
-            cs = _gemm_nt(gs, n, tiles, dev, epi=L.EPI_MASK, mask=None if mask is None else (mask, 0), inv_scale=1.0 / SW, out=out,
-                           colsum=True)
-            return out, cs.sum(0) / SG
 
-        def latent(wi, gb, parts):
-            """latent columns of layer wi: dW = gb (x) code, d code = W[:, cols]^T gb."""
-            for c0, code, acc in parts:
-                n = code.numel()
-                gW[wi][:, c0:c0 + n] = torch.outer(gb, code)
-                acc += W[wi][:, c0:c0 + n].t() @ gb
+def _autodecoder_backward(ctx, g_raw, tiled):
+    """colour branch, trunk, encoding adjoint, deformation MLP: parameter gradients (40) preceded by the three code gradients.
+    tiled = (R, S): the saved planes (and `warped`) are in the tile order of the fused forward."""
+    global _X3
+    _X3 = ctx.x3
+    if ctx.pk is None:
+        raise L.AonError("the tcgen05 training path frees its saved operand planes in backward(): a second backward through the "
+                         "same graph (retain_graph) is not supported -- re-run the forward, or set train_gemm = 'torch'")
+    P, hd, warped, E, V, h, bott, hv = ctx.pk
+    W, (s_, c_, a_), (M, tiles, S) = ctx.W, ctx.codes, ctx.dims
+    dev = g_raw.device
+    SG = float(2 ** int(math.floor(math.log2(max(1, M // S)))))
+    inv_w = 1.0 / (SG * SA)
+    g_raw = g_raw.contiguous()
+    gW = [torch.empty_like(w) for w in W]
+    gB = [None] * 20
+    g_s, g_c, g_a = torch.zeros_like(s_), torch.zeros_like(c_), torch.zeros_like(a_)
 
-        # ---- colour branch ----
-        Gr = _pack_rows(g_raw, M, tiles, 16, SG)
-        Gs = _pack_rows(g_raw[:, 3:], M, tiles, 16, SG)
-        gB[19], gB[18] = g_raw[:, :3].sum(0), g_raw[:, 3:].sum(0)
-        _wgrad_head(hv[3], 128, Gr, 3, gW[19], inv_w)
-        d, cs = dgrad([(Gr, 16, 19, 0)], 128, hv[3], [128], [16])
-        for i in (3, 2, 1):
-            _wgrad(d, 128, hv[i - 1], 0, 128, 128, gW[13 + i], 0, inv_w)
-            gB[13 + i] = cs
-            d, cs = dgrad([(d, 128, 13 + i, 0)], 128, hv[i - 1], [128], [128])
-        _wgrad(d, 128, bott, 0, 256, 256, gW[13], 0, inv_w)
-        _wgrad(d, 128, V, 0, 32, 27, gW[13], 256, inv_w)
-        gB[13] = cs
-        latent(13, gB[13], [(283, c_, g_c)])
-        d_bott, cs = dgrad([(d, 128, 13, 0)], 256, None, [416], [128])
-        # ---- trunk ----
-        _wgrad(d_bott, 256, h[7], 0, 256, 256, gW[17], 0, inv_w)
-        gB[17] = cs
-        _wgrad_head(h[7], 256, Gs, 1, gW[18], inv_w)
-        d, cs = dgrad([(d_bott, 256, 17, 0), (Gs, 16, 18, 0)], 256, h[7], [256, 256], [256, 16])
-        d5 = None
-        for i in range(7, -1, -1):
-            wi = 5 + i
-            x = E if i == 0 else h[i - 1]
-            _wgrad(d, 256, x, 0, 64 if i == 0 else 256, 63 if i == 0 else 256, gW[wi], 0, inv_w)
-            gB[wi] = cs
-            if i == 5:
-                _wgrad(d, 256, E, 0, 64, 63, gW[wi], 256, inv_w)
-                latent(wi, gB[wi], [(319, s_, g_s)])
-                d5 = d
-            if i == 0:
-                latent(wi, gB[wi], [(63, s_, g_s)])
-                break
-            d, cs = dgrad([(d, 256, wi, 0)], 256, h[i - 1], [448 if i == 5 else 256], [256])
-        # ---- encoding -> warped position -> deformation MLP ----
-        g_enc = torch.empty(tiles * 128, 63, dtype=torch.float32, device=dev)
-        W0T, W5T = _pack_linear(W[5], True, 192, 256, SW), _pack_linear(W[10], True, 448, 256, SW)
-        _gemm_nt([(d, 0, 256, W0T, 0, 0), (d5, 0, 256, W5T, 0, 256)], 64, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / (SW * SG),
-                  out_f32=g_enc, n_valid=63)
-        g_warped = L.pos_enc_backward(warped, g_enc[:M], 10)                        # [M,3]; d warped / d delta = 1
-        Gd = _pack_rows(g_warped, M, tiles, 16, SG)
-        gB[4] = g_warped.sum(0)
-        _wgrad_head(hd[3], 128, Gd, 3, gW[4], inv_w)
-        d, cs = dgrad([(Gd, 16, 4, 0)], 128, hd[3], [128], [16])
-        for i in (3, 2, 1):
-            _wgrad(d, 128, hd[i - 1], 0, 128, 128, gW[i], 0, inv_w)
-            gB[i] = cs
-            d, cs = dgrad([(d, 128, i, 0)], 128, hd[i - 1], [128], [128])
-        _wgrad(d, 128, P, 0, 16, 3, gW[0], 0, inv_w)
-        gB[0] = cs
-        latent(0, gB[0], [(3, s_, g_s), (131, a_, g_a)])
-        ctx.pk = None
-        out = [None, None, None, g_s.view(1, -1), g_c.view(1, -1), g_a.view(1, -1)]
-        for w, b in zip(gW, gB):
-            out += [w, b]
-        return tuple(out)
+    def dgrad(segs, n, mask, rows_pad, k_pad):
+        """segs: [(dY, kext, weight index, first row of W^T)] -> (PK(tiles, n) masked by `mask`, its column sums / SG)."""
+        out = _PK(tiles, n, dev)
+        gs = [(dY, 0, k, _pack_linear(W[wi], True, rows_pad[j], k_pad[j], SW), 0, r0) for j, (dY, k, wi, r0) in enumerate(segs)]
+        cs = _gemm_nt(gs, n, tiles, dev, epi=L.EPI_MASK, mask=None if mask is None else (mask, 0), inv_scale=1.0 / SW, out=out,
+                       colsum=True)
+        return out, cs.sum(0) / SG
+
+    def latent(wi, gb, parts):
+        """latent columns of layer wi: dW = gb (x) code, d code = W[:, cols]^T gb."""
+        for c0, code, acc in parts:
+            n = code.numel()
+            gW[wi][:, c0:c0 + n] = torch.outer(gb, code)
+            acc += W[wi][:, c0:c0 + n].t() @ gb
+
+    # ---- colour branch ----
+    Gr = _pack_grad(g_raw, M, tiles, 16, SG, tiled)
+    Gs = _pack_grad(g_raw[:, 3:], M, tiles, 16, SG, tiled)
+    gB[19], gB[18] = g_raw[:, :3].sum(0), g_raw[:, 3:].sum(0)
+    _wgrad_head(hv[3], 128, Gr, 3, gW[19], inv_w)
+    d, cs = dgrad([(Gr, 16, 19, 0)], 128, hv[3], [128], [16])
+    for i in (3, 2, 1):
+        _wgrad(d, 128, hv[i - 1], 0, 128, 128, gW[13 + i], 0, inv_w)
+        gB[13 + i] = cs
+        d, cs = dgrad([(d, 128, 13 + i, 0)], 128, hv[i - 1], [128], [128])
+    _wgrad(d, 128, bott, 0, 256, 256, gW[13], 0, inv_w)
+    _wgrad(d, 128, V, 0, 32, 27, gW[13], 256, inv_w)
+    gB[13] = cs
+    latent(13, gB[13], [(283, c_, g_c)])
+    d_bott, cs = dgrad([(d, 128, 13, 0)], 256, None, [416], [128])
+    # ---- trunk ----
+    _wgrad(d_bott, 256, h[7], 0, 256, 256, gW[17], 0, inv_w)
+    gB[17] = cs
+    _wgrad_head(h[7], 256, Gs, 1, gW[18], inv_w)
+    d, cs = dgrad([(d_bott, 256, 17, 0), (Gs, 16, 18, 0)], 256, h[7], [256, 256], [256, 16])
+    d5 = None
+    for i in range(7, -1, -1):
+        wi = 5 + i
+        x = E if i == 0 else h[i - 1]
+        _wgrad(d, 256, x, 0, 64 if i == 0 else 256, 63 if i == 0 else 256, gW[wi], 0, inv_w)
+        gB[wi] = cs
+        if i == 5:
+            _wgrad(d, 256, E, 0, 64, 63, gW[wi], 256, inv_w)
+            latent(wi, gB[wi], [(319, s_, g_s)])
+            d5 = d
+        if i == 0:
+            latent(wi, gB[wi], [(63, s_, g_s)])
+            break
+        d, cs = dgrad([(d, 256, wi, 0)], 256, h[i - 1], [448 if i == 5 else 256], [256])
+    # ---- encoding -> warped position -> deformation MLP ----
+    g_enc = torch.empty(tiles * 128, 63, dtype=torch.float32, device=dev)
+    W0T, W5T = _pack_linear(W[5], True, 192, 256, SW), _pack_linear(W[10], True, 448, 256, SW)
+    _gemm_nt([(d, 0, 256, W0T, 0, 0), (d5, 0, 256, W5T, 0, 256)], 64, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / (SW * SG),
+              out_f32=g_enc, n_valid=63)
+    # [rows,3]; d warped / d delta = 1.  Fused forward: warped and g_enc are both in tile order (padding rows: zero gradient)
+    g_warped = L.pos_enc_backward(warped, g_enc[:warped.shape[0]], 10)
+    Gd = _pack_rows(g_warped, g_warped.shape[0], tiles, 16, SG)
+    gB[4] = g_warped.sum(0)
+    _wgrad_head(hd[3], 128, Gd, 3, gW[4], inv_w)
+    d, cs = dgrad([(Gd, 16, 4, 0)], 128, hd[3], [128], [16])
+    for i in (3, 2, 1):
+        _wgrad(d, 128, hd[i - 1], 0, 128, 128, gW[i], 0, inv_w)
+        gB[i] = cs
+        d, cs = dgrad([(d, 128, i, 0)], 128, hd[i - 1], [128], [128])
+    _wgrad(d, 128, P, 0, 16, 3, gW[0], 0, inv_w)
+    gB[0] = cs
+    latent(0, gB[0], [(3, s_, g_s), (131, a_, g_a)])
+    ctx.pk = None
+    out = [g_s.view(1, -1), g_c.view(1, -1), g_a.view(1, -1)]
+    for w, b in zip(gW, gB):
+        out += [w, b]
+    return tuple(out)
+
+
+class _AutoDecoderFusedFn(torch.autograd.Function):
+    """(rays_o, rays_d, viewdirs [R,3], t_vals [R,S], view_enc [R,27], precision, shape, appearance, articulation, w0, b0, ...)
+    -> raw [R*S,4]: deformation MLP -> warp -> pos_enc -> trunk -> colour head of the level in ONE launch of the fused render
+    kernel (aon_forward_train; latent columns folded into per-call bias stages by aon_fold_latents), every layer output and the
+    warped positions written once; the backward is _autodecoder_backward on those planes."""
+
+    @staticmethod
+    def forward(ctx, o, d, v, t_vals, view_enc, precision, shape, app, art, *params):
+        ctx.x3 = _X3
+        R, S = t_vals.shape
+        W = [p.detach().contiguous() for p in params[0::2]]
+        B = [p.detach().contiguous() for p in params[1::2]]
+        s_, c_, a_ = shape.detach().reshape(-1), app.detach().reshape(-1), art.detach().reshape(-1)
+        packed = L.pack_weights(L.KIND_AUTODECODER, precision, W, B)
+        folded = L.fold_latents(L.KIND_AUTODECODER, precision, packed, s_.float().contiguous(), c_.float().contiguous(),
+                                a_.float().contiguous())
+        acts, enc, raw, warped = L.forward_train(L.KIND_AUTODECODER, precision, packed, folded, o, d, v, t_vals.contiguous(), S)
+        pos = (o[:, None, :] + t_vals[..., None] * d[:, None, :]).reshape(-1, 3)       # helper.py:25-26 (the kernel's cast_rays)
+        P = L.pack_rows_tiled(pos, R, S, 16, SA, x3=_X3)
+        V = L.pack_rows_tiled(view_enc.detach().contiguous(), R, S, 32, SA, per_ray=True, x3=_X3)
+        ctx.pk = (P, acts[0:4], warped, enc, V, acts[4:12], acts[12], acts[13:17])
+        ctx.W, ctx.codes, ctx.dims = W, (s_, c_, a_), (R * S, enc.m_tiles, S)
+        ctx.tiled = (R, S)
+        return raw
+
+    @staticmethod
+    def backward(ctx, g_raw):
+        return (None,) * 6 + _autodecoder_backward(ctx, g_raw, ctx.tiled)
+
+
+def autodecoder_fused(o, d, v, t_vals, view_enc, latents: dict, mlp, x3: bool = True) -> tuple:
+    """rays [R,3] x 3, t_vals [R,S], view_enc [R,27], latents -> (raw_rgb [R,S,3], raw_sigma [R,S,1]) through the fused chain."""
+    global _X3
+    _X3 = bool(x3)
+    params = []
+    for lin in mlp.linears():
+        params += [lin.weight, lin.bias]
+    R, S = t_vals.shape
+    raw = _AutoDecoderFusedFn.apply(o, d, v, t_vals, view_enc, L.PREC_TC_F16X3 if x3 else L.PREC_TC_F16, latents["density"],
+                                    latents["color"], latents["articulation"], *params)
+    return raw[:, :3].reshape(R, S, 3), raw[:, 3:].reshape(R, S, 1)
 
 
 def autodecoder_mlp(pos: torch.Tensor, view_enc: torch.Tensor, latents: dict, mlp, x3: bool = True) -> tuple:
