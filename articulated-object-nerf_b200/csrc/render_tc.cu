@@ -1017,28 +1017,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
 #pragma unroll
             for (int i = 0; i < 32; ++i) p.dbg[((size_t)ui * 128 + row) * 256 + cc * 32 + i] = v[i] * (1.0f / SCALE_A);
           }
+          // training forward: this thread's 32 outputs go to HBM once, as 4 x 16-byte rows of the packed plane (+ a ReLU mask
+          // word: bit i = pre-activation i is not negative, collected from the sign bits with one funnel shift per value)
+          uint4* gh = nullptr;
+          uint4* gl = nullptr;
+          if (TRAIN) {
+            const size_t tile = (size_t)blockIdx.x * SG + (sb + s);
+            const size_t g0 = (tile * (size_t)(u.n128 * 16) + cc * 4) * 128 + row;
+            gh = p.dump.hi[ui] + g0;
+            if (X3) gl = p.dump.lo[ui] + g0;
+            if (relu && p.dump.bits[ui] != nullptr) {
+              uint32_t neg = 0;
+#pragma unroll
+              for (int i = 31; i >= 0; --i) neg = __funnelshift_l(__float_as_uint(v[i]), neg, 1);
+              p.dump.bits[ui][(tile * 128 + row) * (size_t)(u.n128 * 4) + cc] = ~neg;
+            }
+          }
           if (relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (TRAIN) {
-            const size_t tile = (size_t)blockIdx.x * SG + (sb + s);
-            const int nkg = u.n128 * 16;   // k-groups (8 features) of this unit's output plane
-            if (relu && p.dump.bits[ui] != nullptr) {
-              uint32_t bits = 0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) bits |= (uint32_t)(v[i] > 0.f) << i;
-              p.dump.bits[ui][(tile * 128 + row) * (size_t)(u.n128 * 4) + cc] = bits;
-            }
-            uint4* gh = p.dump.hi[ui] + (tile * nkg + cc * 4) * 128 + row;
-            uint4* gl = X3 ? p.dump.lo[ui] + (tile * nkg + cc * 4) * 128 + row : nullptr;
-#pragma unroll
-            for (int kg = 0; kg < 4; ++kg) {
-              uint4 hi, lo;
-              pack8<X3, BF16>(v + kg * 8, hi, lo);
-              gh[kg * 128] = hi;
-              if (X3) gl[kg * 128] = lo;
-            }
           }
           if (epi == EPI_STORE_SIGMA) {
 #pragma unroll
@@ -1058,6 +1055,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
               h1 = fmaf(w1.x, v[i], h1); h1 = fmaf(w1.y, v[i + 1], h1); h1 = fmaf(w1.z, v[i + 2], h1); h1 = fmaf(w1.w, v[i + 3], h1);
               h2 = fmaf(w2.x, v[i], h2); h2 = fmaf(w2.y, v[i + 1], h2); h2 = fmaf(w2.z, v[i + 2], h2); h2 = fmaf(w2.w, v[i + 3], h2);
             }
+            if (TRAIN) {   // the head's input layer is needed by the backward (wgrad operand of the head, ReLU mask)
+#pragma unroll
+              for (int kg = 0; kg < 4; ++kg) {
+                uint4 hi, lo;
+                pack8<X3, BF16>(v + kg * 8, hi, lo);
+                gh[kg * 128] = hi;
+                if (X3) gl[kg * 128] = lo;
+              }
+            }
           } else {
             // next layer's A operand: 32 hidden features of this row -> chunk cc
 #pragma unroll
@@ -1071,6 +1077,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(lbar(BAR_CHUNK + cc));
             if (tid == 0 && j == 0) mark(1, pl, ui, 1);
+            if (TRAIN) {
+              // The finished chunk (32 features x 128 rows: 8 KB hi + 8 KB lo) sits in shared memory in exactly the layout of
+              // its slice of the packed plane in HBM: once the four warps that wrote it have met (named barrier 7 / 8 of this
+              // half), ONE thread hands it to the TMA engine as two bulk copies -- no per-thread global stores in the
+              // epilogue.  The region is overwritten by the next unit's epilogue, >= 1 such barrier later: the issuing thread
+              // waits for the previous chunk's shared-memory reads before it arrives at the barrier.
+              const bool issuer = quad == 0 && lane == 0;
+              if (issuer) ptx::bulk_wait_read0();
+              __syncwarp();
+              asm volatile("bar.sync %0, 128;" ::"r"(7 + half) : "memory");
+              if (issuer) {
+                const uint32_t src = sm_u32 + OFF_A + cc * 8192;
+                ptx::bulk_s2g(gh - row, src, 8192);
+                if (X3) ptx::bulk_s2g(gl - row, src + LO_A, 8192);
+                ptx::bulk_commit();
+              }
+            }
           }
         }
         if (tid == 0) mark(1, pl, ui, 2);
@@ -1168,6 +1191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
     }
   }
 
+  if (TRAIN && (tid == 0 || tid == 128)) ptx::bulk_wait0();   // the two bulk-store issuers: all activation planes have landed
   // ---- teardown ----
   ptx::tc_fence_before();
   ptx::cluster_sync_all();   // no CTA of the pair may exit (or free TMEM) while its partner can still touch it

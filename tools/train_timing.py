@@ -18,8 +18,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=20)
 dev = torch.device("cuda:0")
 ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph replay of lit.GraphedStep")
+ap.add_argument("--only", default="", help="exp:gemm, e.g. vanilla:tc -- run one configuration only (profiling)")
 args = ap.parse_args()
-for exp, R, gemm in (("vanilla", 2048, "tc"), ("vanilla_autodecoder", 4096, "tc"), ("vanilla", 2048, "tc16"), ("vanilla_autodecoder", 4096, "tc16")):
+CONFIGS = (("vanilla", 2048, "tc"), ("vanilla_autodecoder", 4096, "tc"), ("vanilla", 2048, "tc16"), ("vanilla_autodecoder", 4096, "tc16"))
+if args.only:
+    CONFIGS = tuple(c for c in CONFIGS if "%s:%s" % (c[0], c[2]) == args.only)
+for exp, R, gemm in CONFIGS:
     torch.manual_seed(0)
     s = lit.build_system(SimpleNamespace(exp_type=exp, run_max_steps=1000, white_back=True, N_max_objs=1, N_obj_code_length=128)).to(dev)
     s.train()
