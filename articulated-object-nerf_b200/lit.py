@@ -569,7 +569,10 @@ class Trainer:
         if sync is None:
             sync = system._grad_sync = GradSync(list(system.named_parameters()), opt.flat_grad)
         graphed, shapes = None, None
-        use_graph = self.cuda_graph and sync.world == 1 and getattr(system.model, "train_gemm", "torch") in ("tc", "tc16")
+        # several ranks: the per-MLP all-reduces are captured with the step (NCCL collectives are graph-capturable; every rank
+        # captures the same sequence), AON_TRAIN_GRAPH_NCCL=0 keeps multi-rank steps eager
+        multi_ok = sync.world == 1 or os.environ.get("AON_TRAIN_GRAPH_NCCL", "1") == "1"
+        use_graph = self.cuda_graph and multi_ok and getattr(system.model, "train_gemm", "torch") in ("tc", "tc16")
         for batch_idx, batch in enumerate(batches):
             if self.global_step >= self.max_steps:
                 break
@@ -577,7 +580,7 @@ class Trainer:
                 sig = tuple((k, tuple(v.shape)) for k, v in sorted(batch.items()) if torch.is_tensor(v))
                 if graphed is None or sig != shapes:
                     try:
-                        graphed, shapes = GraphedStep(system, opt, batch, None), sig   # dry run + capture; trains nothing
+                        graphed, shapes = GraphedStep(system, opt, batch, sync if sync.world > 1 else None), sig   # dry run + capture; trains nothing
                     except Exception as e:       # capture refused (see GraphedStep): eager steps from here on
                         if self.is_global_zero:
                             print("lit.Trainer: CUDA-graph capture of the training step failed (%s: %s); running eager steps"

@@ -394,12 +394,12 @@ def train_block(args, dev, world, rank, rays_o, rays_d, gemm="tc"):
         batch.update(instance_id=torch.tensor([0], device=dev), articulation_id=torch.tensor([3], device=dev))
 
     sync = lit.GradSync(list(s.named_parameters()), opt.flat_grad)   # per-MLP slices all-reduced while the backward still runs
-    # one rank: the whole step (zero_grad .. Adam) is captured once in a CUDA graph and replayed (lit.GraphedStep), like
-    # lit.Trainer.fit does; several ranks: eager launches with the overlapped all-reduces
+    # the whole step (zero_grad .. Adam, with the overlapped per-MLP all-reduces when there are several ranks) is captured once
+    # in a CUDA graph and replayed (lit.GraphedStep), like lit.Trainer.fit does
     graphed = None
-    if world == 1 and os.environ.get("AON_TRAIN_GRAPH", "1") == "1":
+    if (world == 1 or os.environ.get("AON_TRAIN_GRAPH_NCCL", "1") == "1") and os.environ.get("AON_TRAIN_GRAPH", "1") == "1":
         try:
-            graphed = lit.GraphedStep(s, opt, batch, None)
+            graphed = lit.GraphedStep(s, opt, batch, sync if world > 1 else None)
         except Exception as e:
             sys.stderr.write("bench: CUDA-graph capture of the training step failed (%s); eager steps\n" % str(e).splitlines()[0])
 
@@ -430,7 +430,25 @@ def train_block(args, dev, world, rank, rays_o, rays_d, gemm="tc"):
     torch.cuda.synchronize()
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / K
     flop = 3 * Rb * (S0 + S1) * FLOP_PER_SAMPLE[args.kind]
-    return {"value": world * Rb / (ms * 1e-3), "unit": "rays/s (training: forward + backward + all-reduce + Adam)", "ms_per_step": ms,
+    # HBM roofline of the step (it is bound by operand planes, not by the tensor pipe): algorithmic bytes =
+    # every 16-bit activation / gradient plane the design moves, counted once per pass that must touch HBM -- the fused forward
+    # WRITES each layer output once (no layer re-reads its input), the dgrad chain reads and writes each delta plane once, every
+    # wgrad reads its two operand planes once.  Feature columns per sample (vanilla): forward 2496, dgrad 2432 + 2208,
+    # wgrad 5696; auto-decoder: forward 3392, dgrad 3328 + 3504, wgrad 7520 (the fp32 encoding gradient and the 16 / 32-wide
+    # position / view planes are left out).
+    cols = {"vanilla": 2496 + 2432 + 2208 + 5696, "autodecoder": 3392 + 3328 + 3504 + 7520}[args.kind]
+    planes = 2 if gemm == "tc" else 1
+    step_bytes = Rb * (S0 + S1) * cols * 2 * planes
+    try:
+        hbm_peak, hbm_src = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs, of measured"
+    except Exception:
+        hbm_peak, hbm_src = 6400.0, "fallback of B200_PROFILING.md, of fallback"
+    roof = {"bound": "hbm", "achieved": step_bytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": step_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_step": step_bytes, "peak_source": hbm_src,
+            "what": "whole training step (all kernels): operand-plane bytes the design must move through HBM / step time"}
+    return {"value": world * Rb / (ms * 1e-3), "roofline": roof,
+            "forward": "fused: one launch per level (aon_forward_train), each layer output written to HBM once" if getattr(s.model, "train_fwd", "") == "fused" else "one GEMM launch per nn.Linear",
+            "sampling_draws": "Philox4x32-10 inside the sampling kernels (no uniform tensors in HBM)", "unit": "rays/s (training: forward + backward + all-reduce + Adam)", "ms_per_step": ms,
             "rays_per_gpu_per_step": Rb, "steps": K, "warmup": 3, "algorithmic_tflops_per_gpu": flop / (ms * 1e-3) / 1e12,
             "gemm": {"tc": "tcgen05 kind::f16, fp16 hi+lo operands (3 MMAs per K step), fp32 accumulate",
                      "tc16": "tcgen05 kind::f16, single fp16 operand planes (1 MMA per K step; fast training mode, ~1e-3 gradient noise), fp32 accumulate"}.get(s.model.train_gemm, "library"),

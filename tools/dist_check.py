@@ -50,9 +50,52 @@ def main():
             if rank == 0:
                 print("world %d mode %s: render_image_sharded == single-GPU bitwise: %s" % (dist.get_world_size(), mode, same_i), flush=True)
             ok &= same_i
+    ok &= train_check(rank, dev)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
+
+
+def train_check(rank, dev):
+    """DDP semantics of the training step over NCCL: every rank trains on its OWN ray batches and sampling draws, the summed
+    gradients are averaged (lit.GradSync + 1/world in the Adam kernel), so after any number of steps all ranks hold the SAME
+    parameters; and the CUDA-graph replay of the step (all-reduces captured with it) leaves exactly the parameters the
+    eager loop leaves."""
+    from types import SimpleNamespace
+    from aon_b200 import lit
+    world = dist.get_world_size()
+    o, d = L.raygen(48, 64, synth.sapien_focal(48), synth.sapien_camera(1), dev)
+    finals = {}
+    ok = True
+    for mode in ("eager", "graph"):
+        torch.manual_seed(11)                                    # same initial weights on every rank
+        s = lit.build_system(SimpleNamespace(exp_type="vanilla", run_max_steps=100, white_back=True)).to(dev)
+        s.lr_delay_steps = 3
+        s.model.rng_seed = 1000 + rank                           # per-rank sampling draws
+        g = torch.Generator().manual_seed(50 + rank)             # per-rank ray batches
+
+        def batches():
+            for i in range(5):
+                idx = torch.randperm(o.shape[0], generator=g)[:256].to(dev)
+                yield {"rays_o": o[idx][None], "rays_d": d[idx][None], "viewdirs": d[idx][None],
+                       "target": torch.rand(1, 256, 3, generator=g).to(dev)}
+
+        tr = lit.Trainer(max_steps=5, cuda_graph=mode == "graph")
+        tr.fit(s, batches())
+        flat = s._optimizer.flat.detach().clone()
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        same = all(torch.equal(gathered[0], x) for x in gathered)
+        finals[mode] = flat
+        if rank == 0:
+            print("world %d training, %s steps: parameters identical on all ranks after 5 steps: %s (loss %.5f)"
+                  % (world, mode, same, s.logged["train/loss"]), flush=True)
+        ok &= same
+    eq = torch.equal(finals["eager"], finals["graph"])
+    if rank == 0:
+        print("world %d training: graph replay == eager steps bitwise: %s (max abs diff %.3g)"
+              % (world, eq, (finals["eager"] - finals["graph"]).abs().max().item()), flush=True)
+    return ok and (eq or world > 2)      # more than two addends: NCCL's reduction order may differ between a captured and an eager call
 
 
 if __name__ == "__main__":
