@@ -714,15 +714,16 @@ __global__ void pack_linear_kernel(const float* __restrict__ W, int out_f, int i
 
 // dst[r, col_off + c] (or dst[c, col_off + r] if transpose) = scale * sum_split partial[split][r][c], fixed summation order.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int rows_pad, int N, float scale,
-                                    float* __restrict__ dst, long ld, int col_off, int rows_valid, int cols_valid, int transpose) {
+                                    float* __restrict__ dst, long ld, int col_off, int rows_valid, int cols_valid, int flags) {
   const int total = rows_pad * N;
+  const bool transpose = flags & 1, accumulate = flags & 2;   // accumulate: dst += (row-tile sub-batches of one backward pass)
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int r = idx / N, c = idx % N;
     if (r >= rows_valid || c >= cols_valid) continue;
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += partial[(long)k * total + idx];
-    if (transpose) dst[(long)c * ld + col_off + r] = s * scale;
-    else dst[(long)r * ld + col_off + c] = s * scale;
+    float* q = transpose ? dst + (long)c * ld + col_off + r : dst + (long)r * ld + col_off + c;
+    *q = accumulate ? *q + s * scale : s * scale;
   }
 }
 

@@ -495,6 +495,16 @@ class PK:
         self.hi = torch.empty(m_tiles * feat * 128, dtype=torch.float16, device=device)
         self.lo = torch.empty_like(self.hi) if x3 else None
 
+    def tiles(self, t0: int, t1: int) -> "PK":
+        """row tiles [t0, t1) as a PK that shares this one's storage (the layout is tile-major: a contiguous slice)"""
+        v = PK.__new__(PK)
+        v.m_tiles, v.feat = t1 - t0, self.feat
+        n = self.feat * 128
+        v.hi = self.hi[t0 * n:t1 * n]
+        v.lo = None if self.lo is None else self.lo[t0 * n:t1 * n]
+        v.bits = None if self.bits is None else self.bits[t0 * 128:t1 * 128]
+        return v
+
     def to_dense(self) -> torch.Tensor:
         """fp32 [rows, feat] (hi + lo), for tests."""
         v = self.hi.float() + (self.lo.float() if self.lo is not None else 0)
@@ -665,12 +675,12 @@ UNIT_OUT = {KIND_VANILLA: [(256, True)] * 8 + [(256, False), (128, True)],
 
 
 def wgrad_reduce(partial: torch.Tensor, scale: float, dst: torch.Tensor, col_off: int, rows_valid: int, cols_valid: int,
-                 transpose: bool = False) -> None:
+                 transpose: bool = False, accumulate: bool = False) -> None:
     lib = load()
     splits, rows_pad, N = partial.shape
     with _on(dst.device):
         _check(lib.aon_wgrad_reduce(partial.data_ptr(), splits, rows_pad, N, float(scale), _ptr(dst, "dst"), dst.stride(0), col_off,
-                                    rows_valid, cols_valid, int(transpose), _stream()), "aon_wgrad_reduce")
+                                    rows_valid, cols_valid, int(transpose) | (2 if accumulate else 0), _stream()), "aon_wgrad_reduce")
 
 
 def colsum_packed(x: PK, splits: int = 16) -> torch.Tensor:

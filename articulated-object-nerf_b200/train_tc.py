@@ -13,6 +13,7 @@ gradient is O(1 / rays) (mean over 3 * rays residuals), so scaled gradients stay
 from __future__ import annotations
 
 import math
+import os
 from typing import List
 
 import torch
@@ -59,20 +60,36 @@ def _pad_bias(b: torch.Tensor, n: int) -> torch.Tensor:
     return out
 
 
+# row tiles per sub-batch of the backward chain (0 = the whole level at once, the default).  MEASURED AND NOT ADOPTED: with 296
+# tiles a 256-wide delta plane of a sub-batch is 39 MB (hi + lo) and stays in L2 between the GEMM that writes it and the two that
+# read it, which halves the HBM traffic of the backward -- but 11 sub-batches turn 60 large launches into 660 small ones, and
+# each costs ~19 us of fill / drain / split-K reduce: vanilla step 7.75 ms -> 14.0 ms (148: 18.3, 444: 12.5, 592: 11.9 ms).
+BWD_TILES = int(os.environ.get("AON_BWD_TILES", "0"))
+
+
+def _splits(m_tiles: int, a_tiles: int) -> int:
+    """split-K factor of a wgrad GEMM: two CTAs per SM on a whole level, one per SM on a sub-batch (every split then still owns
+    >= 4 row tiles, and the fp32 partial tiles stay small next to the operand planes)"""
+    return max(1, (296 if m_tiles > 2 * SPLIT_TILES else 148) // a_tiles)
+
+
+SPLIT_TILES = 296
+
+
 def _wgrad(dY: L.PK, out_valid: int, X: L.PK, x_off: int, n_cols: int, cols_valid: int, dst: torch.Tensor, col_off: int,
-           inv: float) -> None:
-    """dst[0:out_valid, col_off : col_off + cols_valid] = inv * dY^T X[:, x_off : x_off + n_cols]."""
+           inv: float, accumulate: bool = False) -> None:
+    """dst[0:out_valid, col_off : col_off + cols_valid] (+)= inv * dY^T X[:, x_off : x_off + n_cols]."""
     a_tiles = dY.feat // 128
-    part = _gemm_tn(dY, 0, a_tiles, X, x_off, n_cols, max(1, 296 // a_tiles))
-    L.wgrad_reduce(part, inv, dst, col_off, out_valid, cols_valid)
+    part = _gemm_tn(dY, 0, a_tiles, X, x_off, n_cols, _splits(dY.m_tiles, a_tiles))
+    L.wgrad_reduce(part, inv, dst, col_off, out_valid, cols_valid, accumulate=accumulate)
 
 
-def _wgrad_head(X: L.PK, in_valid: int, G: L.PK, out_valid: int, dst: torch.Tensor, inv: float) -> None:
+def _wgrad_head(X: L.PK, in_valid: int, G: L.PK, out_valid: int, dst: torch.Tensor, inv: float, accumulate: bool = False) -> None:
     """Heads (1 / 3 output features, padded to 16): dst[o, i] = inv * sum_m G[m, o] X[m, i] as the transposed product
     (rows = the 128-feature tiles of X, columns = the 16 padded outputs)."""
     a_tiles = X.feat // 128
-    part = _gemm_tn(X, 0, a_tiles, G, 0, 16, max(1, 296 // a_tiles))
-    L.wgrad_reduce(part, inv, dst, 0, in_valid, out_valid, transpose=True)
+    part = _gemm_tn(X, 0, a_tiles, G, 0, 16, _splits(X.m_tiles, a_tiles))
+    L.wgrad_reduce(part, inv, dst, 0, in_valid, out_valid, transpose=True, accumulate=accumulate)
 
 
 class _VanillaMLPFn(torch.autograd.Function):
@@ -150,43 +167,57 @@ def _vanilla_backward(ctx, g_raw, tiled):
     gB = [None] * 12
     gB[11] = g_raw[:, :3].sum(0)
     gB[10] = g_raw[:, 3:].sum(0)
-
-    # rgb_layer: the packed gradient has 4 live columns (r, g, b, sigma); W_r^T padded with zero rows ignores sigma
-    _wgrad_head(hv, 128, Gr, 3, gW[11], inv_w)
+    # transposed weight packs: once per backward pass
     WrT = _pack_linear(W[11], True, 128, 16, SW)
-    d_hv = _PK(tiles, 128, dev)
-    cs = _gemm_nt([(Gr, 0, 16, WrT, 0, 0)], 128, tiles, dev, epi=L.EPI_MASK, mask=(hv, 0), inv_scale=1.0 / SW, out=d_hv, colsum=True)
-    # views_linear.0 : inputs [bottleneck(256), view enc(27)]
-    _wgrad(d_hv, 128, bott, 0, 256, 256, gW[8], 0, inv_w)
-    _wgrad(d_hv, 128, V, 0, 32, 27, gW[8], 256, inv_w)
-    gB[8] = cs.sum(0) / SG
     WvT = _pack_linear(W[8], True, 288, 128, SW)
-    d_bott = _PK(tiles, 256, dev)
-    cs = _gemm_nt([(d_hv, 0, 128, WvT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, inv_scale=1.0 / SW, out=d_bott, colsum=True)
-    # bottleneck_layer and density_layer both read the last trunk activation h[7]
-    _wgrad(d_bott, 256, h[7], 0, 256, 256, gW[9], 0, inv_w)
-    gB[9] = cs.sum(0) / SG
-    _wgrad_head(h[7], 256, Gs, 1, gW[10], inv_w)
     WbT = _pack_linear(W[9], True, 256, 256, SW)
     WdT = _pack_linear(W[10], True, 256, 16, SW)
-    d = _PK(tiles, 256, dev)
-    cs = _gemm_nt([(d_bott, 0, 256, WbT, 0, 0), (Gs, 0, 16, WdT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[7], 0),
-                   inv_scale=1.0 / SW, out=d, colsum=True)
-    # trunk, last layer first: pts_linears.i maps x_i -> h[i], x_0 = E, x_i = h[i-1] (+ E for i = 5)
-    for i in range(7, -1, -1):
-        x = E if i == 0 else h[i - 1]
-        kin = 64 if i == 0 else 256
-        _wgrad(d, 256, x, 0, kin, 63 if i == 0 else 256, gW[i], 0, inv_w)
-        if i == 5:
-            _wgrad(d, 256, E, 0, 64, 63, gW[5], 256, inv_w)
-        gB[i] = cs.sum(0) / SG                           # column sums of d, produced by the GEMM that wrote d
-        if i == 0:
-            break
-        WT = _pack_linear(W[i], True, 320 if i == 5 else 256, 256, SW)
-        nd = _PK(tiles, 256, dev)
-        cs = _gemm_nt([(d, 0, 256, WT, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(h[i - 1], 0), inv_scale=1.0 / SW, out=nd,
-                       colsum=True)
-        d = nd
+    WT = {i: _pack_linear(W[i], True, 320 if i == 5 else 256, 256, SW) for i in range(1, 8)}
+
+    # The chain can run over sub-batches of row tiles (BWD_TILES, see there: measured, off by default); wgrad partial sums then
+    # accumulate over the sub-batches in a fixed order (aon_wgrad_reduce flags & 2): deterministic.
+    step = BWD_TILES if BWD_TILES > 0 else tiles
+    for t0 in range(0, tiles, step):
+        t1 = min(tiles, t0 + step)
+        nt, acc = t1 - t0, t0 > 0
+        Es, Vs, botts, hvs, Grs, Gss = (x.tiles(t0, t1) for x in (E, V, bott, hv, Gr, Gs))
+        hs = [x.tiles(t0, t1) for x in h]
+
+        def bias(i, cs):
+            v = cs.sum(0) / SG
+            gB[i] = gB[i] + v if acc else v
+
+        # rgb_layer: the packed gradient has 4 live columns (r, g, b, sigma); W_r^T padded with zero rows ignores sigma
+        _wgrad_head(hvs, 128, Grs, 3, gW[11], inv_w, acc)
+        d_hv = _PK(nt, 128, dev)
+        cs = _gemm_nt([(Grs, 0, 16, WrT, 0, 0)], 128, nt, dev, epi=L.EPI_MASK, mask=(hvs, 0), inv_scale=1.0 / SW, out=d_hv, colsum=True)
+        # views_linear.0 : inputs [bottleneck(256), view enc(27)]
+        _wgrad(d_hv, 128, botts, 0, 256, 256, gW[8], 0, inv_w, acc)
+        _wgrad(d_hv, 128, Vs, 0, 32, 27, gW[8], 256, inv_w, acc)
+        bias(8, cs)
+        d_bott = _PK(nt, 256, dev)
+        cs = _gemm_nt([(d_hv, 0, 128, WvT, 0, 0)], 256, nt, dev, epi=L.EPI_MASK, inv_scale=1.0 / SW, out=d_bott, colsum=True)
+        # bottleneck_layer and density_layer both read the last trunk activation h[7]
+        _wgrad(d_bott, 256, hs[7], 0, 256, 256, gW[9], 0, inv_w, acc)
+        bias(9, cs)
+        _wgrad_head(hs[7], 256, Gss, 1, gW[10], inv_w, acc)
+        d = _PK(nt, 256, dev)
+        cs = _gemm_nt([(d_bott, 0, 256, WbT, 0, 0), (Gss, 0, 16, WdT, 0, 0)], 256, nt, dev, epi=L.EPI_MASK, mask=(hs[7], 0),
+                       inv_scale=1.0 / SW, out=d, colsum=True)
+        # trunk, last layer first: pts_linears.i maps x_i -> h[i], x_0 = E, x_i = h[i-1] (+ E for i = 5)
+        for i in range(7, -1, -1):
+            x = Es if i == 0 else hs[i - 1]
+            kin = 64 if i == 0 else 256
+            _wgrad(d, 256, x, 0, kin, 63 if i == 0 else 256, gW[i], 0, inv_w, acc)
+            if i == 5:
+                _wgrad(d, 256, Es, 0, 64, 63, gW[5], 256, inv_w, acc)
+            bias(i, cs)                                      # column sums of d, produced by the GEMM that wrote d
+            if i == 0:
+                break
+            nd = _PK(nt, 256, dev)
+            cs = _gemm_nt([(d, 0, 256, WT[i], 0, 0)], 256, nt, dev, epi=L.EPI_MASK, mask=(hs[i - 1], 0), inv_scale=1.0 / SW, out=nd,
+                           colsum=True)
+            d = nd
     ctx.pk = None
     out = []
     for w, b in zip(gW, gB):

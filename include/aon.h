@@ -332,9 +332,10 @@ int aon_pack_rows(const float* src, long ld, int C, long M, int row_div, int m_t
  * (forward); 1: rows = in, k = out (dgrad). */
 int aon_pack_linear(const float* W, int out_features, int in_features, int transpose, int r_pad, int k_pad,
                     float scale, void* hi, void* lo, aon_stream_t stream);
-/* dst[r, col_off + c] (transpose: dst[c, col_off + r]) = scale * sum_split partial[split][r][c], r < rows_valid, c < cols_valid */
+/* dst[r, col_off + c] (flags & 1, transpose: dst[c, col_off + r]) = scale * sum_split partial[split][r][c], r < rows_valid,
+ * c < cols_valid; flags & 2: added to dst instead of overwriting it (row-tile sub-batches of one backward pass) */
 int aon_wgrad_reduce(const float* partial, int splits, int rows_pad, int N, float scale, float* dst, long ld,
-                     int col_off, int rows_valid, int cols_valid, int transpose, aon_stream_t stream);
+                     int col_off, int rows_valid, int cols_valid, int flags, aon_stream_t stream);
 /* column sums of a PK(m_tiles*128, feat) tensor (bias gradients): partial[split][feat], split = contiguous tile ranges */
 int aon_colsum_packed(const void* hi, const void* lo, int feat, int m_tiles, int splits, float* partial,
                       aon_stream_t stream);
