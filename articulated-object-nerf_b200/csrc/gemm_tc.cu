@@ -472,6 +472,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_tc_nt_persistent_kernel(co
     }
     const int n_chunks = N / 32;
     long lt = 0;
+    float cs_acc = 0.f;
+    static_assert(GP_EPI_THREADS >= 256, "one epilogue thread per output column");
     for (long tile = tile0; tile < tile_end; tile += tile_step, ++lt) {
       const int ab = (int)(lt & 1);
       const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)ab * buf_cols;
@@ -588,10 +590,11 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_tc_nt_persistent_kernel(co
         // the eight epilogue warps meet once per tile; s_colsum is double buffered by tile parity, so a warp that runs ahead
         // into the next tile writes the other half
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int c = e; c < N; c += GP_EPI_THREADS)
-          g.colsum[tile * N + c] = (s_colsum[ab][0][c] + s_colsum[ab][1][c]) + (s_colsum[ab][2][c] + s_colsum[ab][3][c]);
+        // one partial row per CTA (not per tile): the column sums of this CTA's tiles accumulate in a register, in tile order
+        if (e < N) cs_acc += (s_colsum[ab][0][e] + s_colsum[ab][1][e]) + (s_colsum[ab][2][e] + s_colsum[ab][3][e]);
       }
     }
+    if (g.colsum && e < N) g.colsum[(long)blockIdx.x * N + e] = cs_acc;
   }
   tc_fence_before();
   __syncthreads();
@@ -713,18 +716,38 @@ __global__ void pack_linear_kernel(const float* __restrict__ W, int out_f, int i
 }
 
 // dst[r, col_off + c] (or dst[c, col_off + r] if transpose) = scale * sum_split partial[split][r][c], fixed summation order.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int rows_pad, int N, float scale,
-                                    float* __restrict__ dst, long ld, int col_off, int rows_valid, int cols_valid, int flags) {
+// A block owns 64 consecutive outputs; its four 64-thread groups each sum a contiguous quarter of the splits (four independent
+// accumulators per thread keep 4 loads in flight), and the quarters are combined in a fixed order through shared memory: four
+// times the memory-level parallelism of one thread per output (148 splits x 256 KB = 39 MB per 256 x 256 layer), same result on
+// every run.
+constexpr int WR_OUT = 64, WR_GROUPS = 4;
+__global__ void __launch_bounds__(WR_OUT * WR_GROUPS)
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int rows_pad, int N, float scale,
+                    float* __restrict__ dst, long ld, int col_off, int rows_valid, int cols_valid, int flags) {
+  __shared__ float s_part[WR_GROUPS][WR_OUT];
   const int total = rows_pad * N;
   const bool transpose = flags & 1, accumulate = flags & 2;   // accumulate: dst += (row-tile sub-batches of one backward pass)
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int r = idx / N, c = idx % N;
-    if (r >= rows_valid || c >= cols_valid) continue;
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[(long)k * total + idx];
-    float* q = transpose ? dst + (long)c * ld + col_off + r : dst + (long)r * ld + col_off + c;
-    *q = accumulate ? *q + s * scale : s * scale;
+  const int tx = threadIdx.x & (WR_OUT - 1), grp = threadIdx.x / WR_OUT;
+  const int idx = blockIdx.x * WR_OUT + tx;
+  const int per = (splits + WR_GROUPS - 1) / WR_GROUPS;
+  const int k0 = grp * per, k1 = min(splits, k0 + per);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (idx < total) {
+    const float* p = partial + idx;
+    int k = k0;
+    for (; k + 3 < k1; k += 4) {
+      a0 += p[(long)k * total]; a1 += p[(long)(k + 1) * total]; a2 += p[(long)(k + 2) * total]; a3 += p[(long)(k + 3) * total];
+    }
+    for (; k < k1; ++k) a0 += p[(long)k * total];
   }
+  s_part[grp][tx] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (grp != 0 || idx >= total) return;
+  const int r = idx / N, c = idx % N;
+  if (r >= rows_valid || c >= cols_valid) return;
+  const float s = (s_part[0][tx] + s_part[1][tx]) + (s_part[2][tx] + s_part[3][tx]);
+  float* q = transpose ? dst + (long)c * ld + col_off + r : dst + (long)r * ld + col_off + c;
+  *q = accumulate ? *q + s * scale : s * scale;
 }
 
 // Column sums of a PK(rows, feat) tensor (hi + lo planes): partial[split][feat] = sum over the split's row tiles.
@@ -812,6 +835,10 @@ static int tmap_packed(const void* base, int feat, int tiles, int groups, CUtens
 
 extern "C" size_t aon_gemm_struct_size(void) { return sizeof(AonGemm); }
 
+static bool nt_persistent(const AonGemm& g, int sms) {
+  return g.mode == AON_GEMM_NT && (g.N == 128 || g.N == 256) && g.m_tiles >= 2 * sms && !(g.reserved & 16);
+}
+
 extern "C" int aon_gemm_tc(const AonGemm* gp, aon_stream_t stream) {
   AON_REQUIRE(gp != nullptr, "aon_gemm_tc: null descriptor");
   const AonGemm& g = *gp;
@@ -860,7 +887,7 @@ extern "C" int aon_gemm_tc(const AonGemm* gp, aon_stream_t stream) {
   }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (g.mode == AON_GEMM_NT && (g.N == 128 || g.N == 256) && g.m_tiles >= 2 * sms && !(g.reserved & 16)) {
+  if (nt_persistent(g, sms)) {
     // the large forward / dgrad GEMMs: persistent kernel, one CTA per SM
     AON_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_nt_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM));
     gemm_tc_nt_persistent_kernel<<<sms, GP_THREADS, GP_SMEM, (cudaStream_t)stream>>>(P);
@@ -871,6 +898,14 @@ extern "C" int aon_gemm_tc(const AonGemm* gp, aon_stream_t stream) {
   gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM, (cudaStream_t)stream>>>(P);
   AON_LAUNCH_CHECK();
   return AON_OK;
+}
+
+// rows of the colsum buffer an NT launch writes: one per row tile, or one per CTA when the persistent kernel takes the GEMM
+extern "C" int aon_gemm_colsum_rows(const AonGemm* gp) {
+  if (!gp) return 0;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return nt_persistent(*gp, sms) ? sms : gp->m_tiles;
 }
 
 extern "C" int aon_pack_rows(const float* src, long ld, int C, long M, int row_div, int m_tiles, int c_pad, float scale, void* hi,
@@ -924,7 +959,7 @@ extern "C" int aon_wgrad_reduce(const float* partial, int splits, int rows_pad, 
                                 int rows_valid, int cols_valid, int transpose, aon_stream_t stream) {
   AON_REQUIRE(partial && dst && splits >= 1 && rows_pad >= 1 && N >= 1, "aon_wgrad_reduce: bad arguments");
   const int total = rows_pad * N;
-  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partial, splits, rows_pad, N, scale, dst, ld, col_off,
+  wgrad_reduce_kernel<<<(total + WR_OUT - 1) / WR_OUT, WR_OUT * WR_GROUPS, 0, (cudaStream_t)stream>>>(partial, splits, rows_pad, N, scale, dst, ld, col_off,
                                                                              rows_valid, cols_valid, transpose);
   AON_LAUNCH_CHECK();
   return AON_OK;

@@ -52,6 +52,7 @@ SYMBOLS = {
     "aon_adam_step_dev": (_i, [_fp, _fp, _fp, _fp, _l, _fp, _vp]),
     "aon_gemm_tc": (_i, [_vp, _vp]),
     "aon_gemm_struct_size": (_sz, []),
+    "aon_gemm_colsum_rows": (_i, [_vp]),
     "aon_pack_rows": (_i, [_fp, _l, _i, _l, _i, _i, _i, _f, _vp, _vp, _vp]),
     "aon_pack_linear": (_i, [_fp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "aon_wgrad_reduce": (_i, [_fp, _i, _i, _i, _f, _fp, _l, _i, _i, _i, _i, _vp]),
@@ -549,8 +550,8 @@ def pack_linear(W: torch.Tensor, transpose: bool, r_pad: int, k_pad: int, scale:
 def gemm_nt(segs, N: int, m_tiles: int, device, *, epi: int = EPI_LINEAR, bias=None, relu: bool = False, mask=None,
             inv_scale: float = 1.0, out_f32: Optional[torch.Tensor] = None, n_valid: int = 0, out: Optional[PK] = None,
             out_off: int = 0, out_scale: float = 1.0, x3: bool = True, colsum: bool = False) -> Optional[torch.Tensor]:
-    """segs: [(A: PK, a_off, kext, B: PW, b_off, b_row0)], all accumulating into D[rows, N].  colsum=True returns the
-    per-tile column sums [m_tiles, N] of the epilogue values (sum over dim 0 = bias gradient)."""
+    """segs: [(A: PK, a_off, kext, B: PW, b_off, b_row0)], all accumulating into D[rows, N].  colsum=True returns partial
+    column sums [rows, N] of the epilogue values (per tile, or per CTA of the persistent kernel; sum over dim 0 = bias gradient)."""
     lib = load()
     g = AonGemm()
     g.mode, g.epi, g.x3, g.nseg, g.N, g.m_tiles = GEMM_NT, epi, int(x3), len(segs), N, m_tiles
@@ -582,7 +583,9 @@ def gemm_nt(segs, N: int, m_tiles: int, device, *, epi: int = EPI_LINEAR, bias=N
             g.relu_bits_out = out.bits.data_ptr()
     cs = None
     if colsum:
-        cs = torch.empty(m_tiles, N, dtype=torch.float32, device=device)
+        with _on(device):
+            rows = lib.aon_gemm_colsum_rows(C.byref(g))        # one partial row per tile, or per CTA of the persistent kernel
+        cs = torch.empty(rows, N, dtype=torch.float32, device=device)
         g.colsum = cs.data_ptr()
     with _on(device):
         _check(lib.aon_gemm_tc(C.byref(g), _stream()), "aon_gemm_tc(NT)")

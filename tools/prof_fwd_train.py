@@ -22,10 +22,15 @@ def timeit(fn, n=20):
         fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
+ONLY = os.environ.get("AON_PROF_ONLY", "")          # e.g. "train" under ncu: training forward launches only
 for name, prec in (("f16x3", L.PREC_TC_F16X3), ("f16", L.PREC_TC_F16)):
     packed = L.pack_weights(L.KIND_VANILLA, prec, W, B)
     for S in (65, 193):
         t = (2.0 + 4.0 * torch.rand(R, S, device=dev)).sort(-1).values.contiguous()
+        if ONLY == "train":                  # profiling: just the training forward (coarse then fine), once
+            L.forward_train(L.KIND_VANILLA, prec, packed, None, o, d, d, t, S)
+            torch.cuda.synchronize()
+            continue
         ms_eval = timeit(lambda: L.render_level(L.KIND_VANILLA, prec, packed, None, o, d, d, t, True))
         ms_train = timeit(lambda: L.forward_train(L.KIND_VANILLA, prec, packed, None, o, d, d, t, S))
         planes = (2 if name == "f16x3" else 1)
