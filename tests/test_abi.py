@@ -102,3 +102,33 @@ def test_gemm_descriptor_mirror_and_training_argument_errors(built_lib):
     assert lib.aon_pos_enc(None, 1, 10, None, None) == -1
     assert lib.aon_adam_step(None, None, None, None, 1, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
     assert lib.aon_pack_rows(None, 1, 1, 1, 1, 1, 8, ctypes.c_float(1.0), None, None, None) == -1
+
+
+def test_round2_entry_points_argument_errors_and_mirrors(built_lib):
+    """The entry points added in round 2 -- in-kernel random draws, the fused training forward, tiled packing, graph-capturable
+    Adam -- reject bad arguments before touching CUDA, their ctypes struct mirrors have the C layout the header documents, and
+    aon_train_tiles / aon_adam_scalars (pure host functions) return the documented values."""
+    import math
+    lib = built_lib.load()
+    assert ctypes.sizeof(built_lib.AonRng) == 24
+    assert ctypes.sizeof(built_lib.AonTrainDump) == (3 * 28 + 4) * 8
+    # row tiles of the fused training forward: 2 * ceil(R / 256) * S
+    assert lib.aon_train_tiles(2048, 65) == 16 * 65 and lib.aon_train_tiles(96, 65) == 2 * 65
+    assert lib.aon_train_tiles(300, 193) == 4 * 193 and lib.aon_train_tiles(0, 65) == 0
+    assert lib.aon_sample_along_rays_rng(2.0, 6.0, 65, None, 4, None, None) == -1 and b"rng" in lib.aon_last_error()
+    assert lib.aon_sample_pdf_rng(None, 0, None, None, 4, 65, 128, None, None) == -1
+    assert lib.aon_rng_uniform(None, 0, 4, 4, None, None) == -1
+    assert lib.aon_rng_advance(None, 1, None) == -1 and b"null" in lib.aon_last_error()
+    assert lib.aon_forward_train(0, 1, None, None, None, None, None, None, 0, 4, 65, None, None) == -1
+    assert lib.aon_forward_train(7, 1, None, None, None, None, None, None, 0, 4, 65, None, None) == -1 and b"kind" in lib.aon_last_error()
+    assert lib.aon_pack_rows_tiled(None, 4, 4, 4, 65, 0, 16, 1.0, None, None, None) == -1
+    assert lib.aon_unpack_rows_tiled(None, 4, 4, 4, 65, None, None) == -1
+    assert lib.aon_adam_step_dev(None, None, None, None, 10, None, None) == -1
+    assert lib.aon_gemm_colsum_rows(None) == 0
+    # aon_adam_scalars: exactly the scalars aon_adam_step derives (torch.optim.Adam's single-tensor formulas)
+    out = (ctypes.c_float * 7)()
+    assert lib.aon_adam_scalars(5e-4, 0.9, 0.999, 1e-8, 3, 0.5, out) == 0
+    bc1, bc2 = 1 - 0.9 ** 3, 1 - 0.999 ** 3
+    want = [1 - 0.9, 0.999, 1 - 0.999, 1e-8, 5e-4 / bc1, math.sqrt(bc2), 0.5]
+    assert all(abs(a - b) <= 1e-6 * abs(b) for a, b in zip(out, want)), (list(out), want)
+    assert lib.aon_adam_scalars(5e-4, 0.9, 0.999, 1e-8, 0, 1.0, out) == -1
