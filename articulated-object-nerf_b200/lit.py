@@ -548,6 +548,10 @@ class Trainer:
         """Continue a run from a checkpoint written by run.save_checkpoint: the step count (LR warm-up / decay position)
         and the Adam moments + bias-correction step.  The weights were loaded by the caller (load_state_dict)."""
         self.global_step = int(blob.get("global_step", 0))
+        # the in-kernel sampling draws are a function of (seed, step): continue where the checkpointed run stopped
+        system.model.rng_offset0 = self.global_step
+        if getattr(system.model, "_rng", None) is not None:
+            system.model._rng.offset_dev.fill_(self.global_step)
         states = blob.get("optimizer_states") or []
         if states:
             opt = getattr(system, "_optimizer", None) or system.configure_optimizers()

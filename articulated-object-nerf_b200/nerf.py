@@ -303,6 +303,7 @@ class _LevelLoop(nn.Module):
             from . import dist as D
             seed = getattr(self, "rng_seed", None)
             r = self._rng = L.Rng((torch.initial_seed() + D.world()[0]) if seed is None else seed, device)
+            r.offset_dev.fill_(int(getattr(self, "rng_offset0", 0)))     # a resumed run continues the draw sequence (one offset per step)
         return r
 
     def _render_autograd(self, o, d, v, t0, u, white_bkgd, latents, rng=None):

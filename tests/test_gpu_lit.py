@@ -94,3 +94,44 @@ def test_graphed_step_equals_eager(built_lib, exp, randomized):
     assert torch.equal(flats[0][0], flats[1][0]), (flats[0][0] - flats[1][0]).abs().max().item()
     assert torch.equal(flats[0][1], flats[1][1])
     assert flats[0][2] == flats[1][2]
+
+
+def test_resume_continues_bitwise(built_lib):
+    """A run resumed from a checkpoint (weights + lit.FlatAdam.state_dict() + global_step, the blob run.save_checkpoint writes)
+    continues EXACTLY where the first run stopped: 3 steps + resume + 3 steps leave the parameters of 6 straight steps, with
+    the randomized sampling on -- the learning-rate schedule, the Adam moments / bias corrections and the in-kernel Philox draw
+    sequence (one offset per step) are all functions of the restored step count."""
+    import copy
+    from aon_b200 import lit
+    dev = torch.device("cuda:0")
+    rays = {k: v.to(dev) for k, v in O.sapien_rays(24, 32, seed=5).items()}
+    g = torch.Generator().manual_seed(1)
+    target = torch.rand(rays["rays_o"].shape[0], 3, generator=g).to(dev)
+
+    def batches(lo, hi):
+        for i in range(lo, hi):
+            sl = slice(128 * i, 128 * (i + 1))
+            b = {k: v[sl][None] for k, v in rays.items()}
+            b["target"] = target[sl][None]
+            yield b
+
+    def fresh():
+        torch.manual_seed(0)
+        s = lit.build_system(_hp("vanilla")).to(dev)
+        s.randomized, s.lr_delay_steps = True, 4
+        s.model.rng_seed = 9
+        return s
+
+    a = fresh()
+    lit.Trainer(max_steps=6).fit(a, batches(0, 6))
+    b = fresh()
+    tr = lit.Trainer(max_steps=3)
+    tr.fit(b, batches(0, 3))
+    blob = copy.deepcopy({"state_dict": b.state_dict(), "global_step": tr.global_step, "optimizer_states": [b._optimizer.state_dict()]})
+    c = fresh()
+    c.load_state_dict(blob["state_dict"])
+    tr2 = lit.Trainer(max_steps=6)
+    tr2.resume(c, blob)
+    tr2.fit(c, batches(3, 6))
+    assert tr2.global_step == 6
+    assert torch.equal(a._optimizer.flat, c._optimizer.flat), (a._optimizer.flat - c._optimizer.flat).abs().max().item()
