@@ -32,6 +32,7 @@
 // Precision modes: AON_PREC_TC_F16 / _BF16 = one MMA per K step; AON_PREC_TC_F16X3 = operands split
 // into fp16 hi + fp16 lo (about 22 significand bits), three MMAs per K step
 // (hi*hi + lo*hi + hi*lo) with fp32 accumulation -- the mode that meets the 1e-4 parity bar.
+#include <stdlib.h>
 #include <string.h>
 
 #include "aon_common.cuh"
@@ -355,6 +356,7 @@ struct TrainDump {
   uint4* e_lo;
   float4* raw;                 // [R * S] in ray-major order: (r, g, b) before the sigmoid, raw density
   float* warped;               // auto-decoder: [tiles * 128][3] warped positions, tile order
+  int dbg_flags;               // profiling experiments only (AON_TRAIN_DEBUG): 1 = no plane stores, 2 = no mask words, 4 = no chunk barrier
 };
 
 struct TcParams {
@@ -1026,7 +1028,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
             const size_t g0 = (tile * (size_t)(u.n128 * 16) + cc * 4) * 128 + row;
             gh = p.dump.hi[ui] + g0;
             if (X3) gl = p.dump.lo[ui] + g0;
-            if (relu && p.dump.bits[ui] != nullptr) {
+            if (relu && p.dump.bits[ui] != nullptr && !(p.dump.dbg_flags & 2)) {
               uint32_t neg = 0;
 #pragma unroll
               for (int i = 31; i >= 0; --i) neg = __funnelshift_l(__float_as_uint(v[i]), neg, 1);
@@ -1086,11 +1088,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) render_tc_kernel(const __grid_c
               const bool issuer = quad == 0 && lane == 0;
               if (issuer) ptx::bulk_wait_read0();
               __syncwarp();
-              asm volatile("bar.sync %0, 128;" ::"r"(7 + half) : "memory");
-              if (issuer) {
+              if (!(p.dump.dbg_flags & 4)) asm volatile("bar.sync %0, 128;" ::"r"(7 + half) : "memory");
+              if (issuer && !(p.dump.dbg_flags & 1)) {
                 const uint32_t src = sm_u32 + OFF_A + cc * 8192;
-                ptx::bulk_s2g(gh - row, src, 8192);
-                if (X3) ptx::bulk_s2g(gl - row, src + LO_A, 8192);
+                // evict_first: 4 GB of planes stream out per level through the L2 that serves the weight stream of every sample
+                // plane; without the hint the level takes 1.53 ms instead of 1.27 ms (measured; evict_last on the weights: no gain)
+                // (the one-pass mode writes half the bytes and has a deeper weight ring: the hint does not pay there -- 0.71 vs 0.74 ms)
+                if (X3) {
+                  const uint64_t pol = ptx::l2_policy_evict_first();
+                  ptx::bulk_s2g_hint(gh - row, src, 8192, pol);
+                  ptx::bulk_s2g_hint(gl - row, src + LO_A, 8192, pol);
+                } else {
+                  ptx::bulk_s2g(gh - row, src, 8192);
+                }
                 ptx::bulk_commit();
               }
             }
@@ -1535,6 +1545,7 @@ extern "C" int aon_forward_train(int kind, int precision, const void* packed, co
     td.hi[i] = (uint4*)d->act_hi[i]; td.lo[i] = (uint4*)d->act_lo[i]; td.bits[i] = (uint32_t*)d->relu_bits[i];
   }
   td.e_hi = (uint4*)d->enc_hi; td.e_lo = (uint4*)d->enc_lo; td.raw = (float4*)d->raw; td.warped = d->warped;
+  if (const char* e = getenv("AON_TRAIN_DEBUG")) td.dbg_flags = atoi(e);   // profiling experiments (tools/prof_fwd_train.py); results are wrong
   return forward_train_tc(kind, precision, packed, folded, rays_o, rays_d, viewdirs, t_vals, t_stride, R, S, td, (cudaStream_t)stream);
 }
 
