@@ -30,6 +30,12 @@ def t(fn, name, flop):
 flop = 2.0 * M * 256 * 256
 t(lambda: L.gemm_nt([(A, 0, 256, B, 0, 0)], 256, tiles, dev, bias=b, relu=True, inv_scale=1 / 512, out=out, out_scale=8.0), "NT forward 256x256", flop)
 t(lambda: L.gemm_nt([(G, 0, 256, B, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(A, 0), inv_scale=1 / 64, out=out, colsum=True), "NT dgrad+mask+colsum", flop)
+out2 = L.PK(tiles, 256, dev)
+assert out.bits is not None            # ReLU bit plane written by the forward call above
+t(lambda: L.gemm_nt([(G, 0, 256, B, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(out, 0), inv_scale=1 / 64, out=out2, colsum=True), "NT dgrad, bit mask + colsum", flop)
+t(lambda: L.gemm_nt([(G, 0, 256, B, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, mask=(out, 0), inv_scale=1 / 64, out=out2), "NT dgrad, bit mask", flop)
+t(lambda: L.gemm_nt([(G, 0, 256, B, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, inv_scale=1 / 64, out=out2, colsum=True), "NT dgrad, colsum only", flop)
+t(lambda: L.gemm_nt([(G, 0, 256, B, 0, 0)], 256, tiles, dev, epi=L.EPI_MASK, inv_scale=1 / 64, out=out2), "NT dgrad, plain", flop)
 t(lambda: L.gemm_tn(G, 0, 2, A, 0, 256, 148), "TN wgrad 256x256", flop)
 
 # single-plane operands (x3 = False): one MMA per K step, half the operand bytes
