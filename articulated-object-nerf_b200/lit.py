@@ -340,6 +340,10 @@ class GraphedStep:
         for k, v in batch.items():
             if torch.is_tensor(v) and v.is_cuda:
                 self.static[k].copy_(v, non_blocking=True)
+            elif torch.is_tensor(v) and not torch.equal(v, self.static[k]):
+                # a host tensor was read (if at all) while the graph was captured: its value is baked into the replay
+                raise L.AonError("GraphedStep: batch['%s'] is a host tensor whose value changed since the capture; pass it as a "
+                                 "CUDA tensor (the reference's datasets do) or run eager steps (AON_TRAIN_GRAPH=0)" % k)
         self._refresh_scalars()
         self.opt.steps += 1                   # the captured opt.step() does not run Python on replay
         self.graph.replay()
