@@ -750,6 +750,20 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int rows_pad,
   *q = accumulate ? *q + s * scale : s * scale;
 }
 
+// bias gradient from the partial column sums of a dgrad GEMM: dst[c] = scale * sum_r partial[r][c], rows summed in order
+// (one thread per column, four accumulators: the rows are few -- one per CTA of the persistent kernel -- and coalesced)
+__global__ void colsum_finish_kernel(const float* __restrict__ partial, int rows, int N, float scale, float* __restrict__ dst) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int r = 0;
+  for (; r + 3 < rows; r += 4) {
+    a0 += partial[(long)r * N + c]; a1 += partial[(long)(r + 1) * N + c]; a2 += partial[(long)(r + 2) * N + c]; a3 += partial[(long)(r + 3) * N + c];
+  }
+  for (; r < rows; ++r) a0 += partial[(long)r * N + c];
+  dst[c] = ((a0 + a1) + (a2 + a3)) * scale;
+}
+
 // Column sums of a PK(rows, feat) tensor (hi + lo planes): partial[split][feat] = sum over the split's row tiles.
 __global__ void __launch_bounds__(128) colsum_packed_kernel(const uint4* __restrict__ hi, const uint4* __restrict__ lo, int feat,
                                                              int m_tiles, int tiles_per_split, float* __restrict__ partial) {
@@ -961,6 +975,13 @@ extern "C" int aon_wgrad_reduce(const float* partial, int splits, int rows_pad, 
   const int total = rows_pad * N;
   wgrad_reduce_kernel<<<(total + WR_OUT - 1) / WR_OUT, WR_OUT * WR_GROUPS, 0, (cudaStream_t)stream>>>(partial, splits, rows_pad, N, scale, dst, ld, col_off,
                                                                              rows_valid, cols_valid, transpose);
+  AON_LAUNCH_CHECK();
+  return AON_OK;
+}
+
+extern "C" int aon_colsum_finish(const float* partial, int rows, int N, float scale, float* dst, aon_stream_t stream) {
+  AON_REQUIRE(partial && dst && rows >= 1 && N >= 1, "aon_colsum_finish: bad arguments");
+  colsum_finish_kernel<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(partial, rows, N, scale, dst);
   AON_LAUNCH_CHECK();
   return AON_OK;
 }

@@ -53,6 +53,7 @@ SYMBOLS = {
     "aon_gemm_tc": (_i, [_vp, _vp]),
     "aon_gemm_struct_size": (_sz, []),
     "aon_gemm_colsum_rows": (_i, [_vp]),
+    "aon_colsum_finish": (_i, [_fp, _i, _i, _f, _fp, _vp]),
     "aon_pack_rows": (_i, [_fp, _l, _i, _l, _i, _i, _i, _f, _vp, _vp, _vp]),
     "aon_pack_linear": (_i, [_fp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "aon_wgrad_reduce": (_i, [_fp, _i, _i, _i, _f, _fp, _l, _i, _i, _i, _i, _vp]),
@@ -684,6 +685,16 @@ def wgrad_reduce(partial: torch.Tensor, scale: float, dst: torch.Tensor, col_off
     with _on(dst.device):
         _check(lib.aon_wgrad_reduce(partial.data_ptr(), splits, rows_pad, N, float(scale), _ptr(dst, "dst"), dst.stride(0), col_off,
                                     rows_valid, cols_valid, int(transpose) | (2 if accumulate else 0), _stream()), "aon_wgrad_reduce")
+
+
+def colsum_finish(partial: torch.Tensor, scale: float) -> torch.Tensor:
+    """partial column sums [rows, N] of a dgrad GEMM (gemm_nt(colsum=True)) -> bias gradient [N] = scale * sum over rows."""
+    lib = load()
+    rows, N = partial.shape
+    out = torch.empty(N, dtype=torch.float32, device=partial.device)
+    with _on(partial.device):
+        _check(lib.aon_colsum_finish(_ptr(partial, "partial"), rows, N, float(scale), _ptr(out), _stream()), "aon_colsum_finish")
+    return out
 
 
 def colsum_packed(x: PK, splits: int = 16) -> torch.Tensor:

@@ -184,7 +184,7 @@ def _vanilla_backward(ctx, g_raw, tiled):
         hs = [x.tiles(t0, t1) for x in h]
 
         def bias(i, cs):
-            v = cs.sum(0) / SG
+            v = L.colsum_finish(cs, 1.0 / SG)
             gB[i] = gB[i] + v if acc else v
 
         # rgb_layer: the packed gradient has 4 live columns (r, g, b, sigma); W_r^T padded with zero rows ignores sigma
@@ -359,7 +359,7 @@ def _autodecoder_backward(ctx, g_raw, tiled):
         gs = [(dY, 0, k, _pack_linear(W[wi], True, rows_pad[j], k_pad[j], SW), 0, r0) for j, (dY, k, wi, r0) in enumerate(segs)]
         cs = _gemm_nt(gs, n, tiles, dev, epi=L.EPI_MASK, mask=None if mask is None else (mask, 0), inv_scale=1.0 / SW, out=out,
                        colsum=True)
-        return out, cs.sum(0) / SG
+        return out, L.colsum_finish(cs, 1.0 / SG)
 
     def latent(wi, gb, parts):
         """latent columns of layer wi: dW = gb (x) code, d code = W[:, cols]^T gb."""

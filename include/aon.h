@@ -335,6 +335,8 @@ int aon_pack_linear(const float* W, int out_features, int in_features, int trans
 /* number of rows of the `colsum` buffer an AON_GEMM_NT launch described by g writes (each row = N partial column sums, summed by
  * the caller in row order): one per row tile, or one per CTA when the persistent kernel takes the GEMM (large N = 128 / 256) */
 int aon_gemm_colsum_rows(const AonGemm* g);
+/* bias gradient from those partial rows: dst[c] = scale * sum_r partial[r][c] (rows summed in order: deterministic) */
+int aon_colsum_finish(const float* partial, int rows, int N, float scale, float* dst, aon_stream_t stream);
 /* dst[r, col_off + c] (flags & 1, transpose: dst[c, col_off + r]) = scale * sum_split partial[split][r][c], r < rows_valid,
  * c < cols_valid; flags & 2: added to dst instead of overwriting it (row-tile sub-batches of one backward pass) */
 int aon_wgrad_reduce(const float* partial, int splits, int rows_pad, int N, float scale, float* dst, long ld,
