@@ -34,6 +34,10 @@ def _t(x):
 
 
 def relerr(a, b, floor=1e-2):
+    """max |a - b| / max(|b|, floor).  DECLARED: the denominator is clamped at 1e-2, i.e. values below 0.01 (dark pixels, empty
+    rays' accumulation) are held to an ABSOLUTE bar of 1e-6 = 1e-4 x 1e-2 instead of a relative one -- BASELINE.md 4.4 writes a
+    1e-6 floor, which would turn fp32 rounding noise of near-zero outputs into O(1) "relative" errors.  bench.py's `parity`
+    block reports the e2e error with both floors."""
     a, b = a.double(), b.double()
     return ((a - b).abs() / b.abs().clamp_min(floor)).max().item()
 
