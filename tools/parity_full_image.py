@@ -61,7 +61,10 @@ for mode in ("f16x3", "fp32", "f16"):
         torch.quantile(worst, 0.9999).item() if n_rays <= 16_000_000 else float("nan"), -10 * torch.log10(torch.tensor(max(mse, 1e-30))).item()))
     if mode == "f16x3":
         bad = (worst > 1e-4).nonzero().flatten()
-        if 0 < bad.numel() <= 4096:
+        n_bad = bad.numel()
+        if n_bad > 2048:                         # float64 is slow on the host: a fixed random subset of the rays above the bar
+            bad = bad[torch.randperm(n_bad, generator=torch.Generator().manual_seed(0))[:2048]]
+        if n_bad > 0:
             # the rays above the bar, evaluated in float64 (oracle restatement of the reference): how far is the reference's OWN
             # fp32 result from that truth on the same rays?
             sd64 = {k: t.double() for k, t in sd.items()}
@@ -72,7 +75,7 @@ for mode in ("f16x3", "fp32", "f16"):
                                 / t64[j].reshape(bad.numel(), -1).abs().clamp_min(1e-2)).max(1).values
             ref_far = torch.stack([r64(ref[j], j) for j in range(3)], 1).max(1).values
             our_far = torch.stack([r64(got[j], j) for j in range(3)], 1).max(1).values
-            outlier_note = ("The %d rays above 1e-4 in `f16x3`, against a float64 evaluation of the same network on those rays: the reference's own "
+            outlier_note = ("%d rays are above 1e-4 in `f16x3`.  " % n_bad) + ("The %d of them evaluated in float64 (the same network, oracle restatement): the reference's own "
                             "fp32 result is off by up to %.2e (median %.2e, %d of them above 1e-4), ours by up to %.2e (median %.2e) -- these are the "
                             "rays on which the fine level is discontinuous in the coarse weights (an importance sample crossing a bin edge), for "
                             "ANY fp32 evaluation." % (bad.numel(), ref_far.max(), ref_far.median(), int((ref_far > 1e-4).sum()), our_far.max(), our_far.median()))
