@@ -1,10 +1,14 @@
-"""Training-path MLP on the tcgen05 GEMMs of csrc/gemm_tc.cu (stage 2).
+"""Training-path MLP on the tcgen05 kernels.
 
-``vanilla_mlp(enc, view_enc, S, mlp)`` evaluates NeRFMLP.forward (models/vanilla_nerf/model.py:95-120) for training:
-every nn.Linear runs as an ``aon_gemm_tc`` launch on packed fp16 hi+lo planes (3 MMAs per K step, fp32 accumulation:
-fp32-grade results), and the backward -- written by hand, no autograd inside -- runs the dgrad chain with the ReLU mask
-in the GEMM epilogue, the weight gradients as split-K tcgen05 GEMMs that read the saved activation / gradient planes as
-MN-major operands, and the bias gradients as packed column sums.
+Forward (default, ``train_fwd = "fused"``): ``vanilla_fused`` / ``autodecoder_fused`` run cast_rays + pos_enc + the whole MLP
+chain of a level (NeRFMLP.forward, models/vanilla_nerf/model.py:95-120; NeRFMLP_AE.forward, model_autodecoder.py:171-239) in
+ONE launch of the fused render kernel (``aon_forward_train``): activations move from layer to layer through shared memory /
+TMEM and every layer output is written to HBM once, as the packed fp16 hi+lo planes (+ ReLU bit planes) the backward reads.
+``vanilla_mlp`` / ``autodecoder_mlp`` (``train_fwd = "layers"``) run every nn.Linear as an ``aon_gemm_tc`` launch instead.
+
+Backward (both): written by hand, no autograd inside -- the dgrad chain with the ReLU mask in the GEMM epilogue, the weight
+gradients as split-K tcgen05 GEMMs that read the saved activation / gradient planes as MN-major operands, the bias gradients
+as column sums produced by the dgrad GEMMs (3 MMAs per K step on hi+lo planes, fp32 accumulation: fp32-grade results).
 
 Scaling (exact powers of two, so nothing is lost): activations x8, weights x64 (the fused render kernel's choice, which
 keeps the lo planes out of the fp16 subnormal range) and gradients x SG with SG = 2^floor(log2(rays)) -- the loss
