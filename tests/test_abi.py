@@ -132,3 +132,18 @@ def test_round2_entry_points_argument_errors_and_mirrors(built_lib):
     want = [1 - 0.9, 0.999, 1 - 0.999, 1e-8, 5e-4 / bc1, math.sqrt(bc2), 0.5]
     assert all(abs(a - b) <= 1e-6 * abs(b) for a, b in zip(out, want)), (list(out), want)
     assert lib.aon_adam_scalars(5e-4, 0.9, 0.999, 1e-8, 0, 1.0, out) == -1
+
+
+def test_training_dump_table_matches_the_kernel_program(built_lib):
+    """lib.UNIT_OUT (the (out features, relu) list forward_train sizes its activation planes from) has one entry per GEMM unit
+    of the fused kernel's program, with the widths of the reference's layer table (aon_layer_shape) in unit order."""
+    L = built_lib
+    for kind, order in ((L.KIND_VANILLA, [0, 1, 2, 3, 4, 5, 6, 7, 9, 8]),                          # csrc/aon_spec.h V_GEMM[].src
+                        (L.KIND_AUTODECODER, [0, 1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12, 17, 13, 14, 15, 16])):   # A_GEMM[].src
+        info = L.debug_program_info(kind, L.PREC_TC_F16X3)
+        assert info["n_units"] == len(L.UNIT_OUT[kind]) == len(order) <= 28
+        shapes = L.layer_shapes(kind)
+        for (n_out, relu), src in zip(L.UNIT_OUT[kind], order):
+            assert shapes[src][0] == n_out, (kind, src, shapes[src], n_out)
+        # the only unit without a ReLU is the bottleneck layer (model.py:112; model_autodecoder.py:229)
+        assert [r for _, r in L.UNIT_OUT[kind]].count(False) == 1
