@@ -404,27 +404,59 @@ class _LitCommon(LitModel):
         return {"name": name, "mean": m, "test": m}
 
     @torch.no_grad()
+    def ssim_each(self, preds, gts):
+        """interface.py:102-112: piqa.SSIM() of every (pred, gt) pair of [H,W,3] images clipped to [0,1].  piqa is not in this
+        image; the metric is restated here from its definition (Wang et al. 2004 with piqa's defaults: 11-tap Gaussian window,
+        sigma 1.5, separable, no padding, k1 = 0.01, k2 = 0.03, value range 1, mean over channels and pixels)."""
+        k = torch.arange(11, dtype=torch.float32) - 5.0
+        k = torch.exp(-k ** 2 / (2 * 1.5 ** 2))
+        k = k / k.sum()
+        out = []
+        for pred, gt in zip(preds, gts):
+            x = torch.clip(pred.permute(2, 0, 1).unsqueeze(0).float(), 0, 1)
+            y = torch.clip(gt.permute(2, 0, 1).unsqueeze(0).float(), 0, 1)
+            C = x.shape[1]
+            wv, wh = k.to(x.device).view(1, 1, 11, 1).repeat(C, 1, 1, 1), k.to(x.device).view(1, 1, 1, 11).repeat(C, 1, 1, 1)
+            blur = lambda t: torch.nn.functional.conv2d(torch.nn.functional.conv2d(t, wv, groups=C), wh, groups=C)
+            mu_x, mu_y = blur(x), blur(y)
+            mu_xx, mu_yy, mu_xy = mu_x ** 2, mu_y ** 2, mu_x * mu_y
+            s_xx, s_yy, s_xy = blur(x ** 2) - mu_xx, blur(y ** 2) - mu_yy, blur(x * y) - mu_xy
+            c1, c2 = 0.01 ** 2, 0.03 ** 2
+            cs = (2 * s_xy + c2) / (s_xx + s_yy + c2)
+            ss = (2 * mu_xy + c1) / (mu_xx + mu_yy + c1) * cs
+            out.append(ss.flatten(1).mean(-1).mean())
+        return torch.stack(out)
+
+    @torch.no_grad()
+    def ssim(self, preds, gts, i_train=None, i_val=None, i_test=None):
+        m = self.ssim_each(preds, gts).mean().item()
+        return {"name": "SSIM", "mean": m, "test": m}
+
+    @torch.no_grad()
     def test_epoch_end(self, outputs):
         """outputs: list of test_step dicts, one per image ([H*W,3] rgb / target, [H*W] instance_mask).  Regroups them
         per image (every rank renders whole images here, so the reference's per-pixel all_gather interleave,
-        interface.py:31-51, is not needed), computes PSNR and object-masked PSNR, and on the global-zero rank writes
-        ckpts/{exp_name}/{render_name}/imageNNN.jpg and ckpts/{exp_name}/results.json.  SSIM / LPIPS need piqa (absent)."""
+        interface.py:31-51, is not needed), computes PSNR, SSIM and object-masked PSNR, and on the global-zero rank writes
+        ckpts/{exp_name}/{render_name}/imageNNN.jpg and ckpts/{exp_name}/results.json (model.py:459-507).  LPIPS needs the
+        pretrained VGG weights piqa downloads (no network here): not computed, and not written."""
         W, H = self.hparams.img_wh
         rgbs = [o["rgb"].reshape(H, W, 3) for o in outputs]
         targets = [o["target"].reshape(H, W, 3) for o in outputs]
         masks = [o["instance_mask"].reshape(H, W).bool() for o in outputs]
         psnr = self.psnr(rgbs, targets)
+        ssim = self.ssim(rgbs, targets) if min(H, W) >= 11 else {"name": "SSIM", "mean": float("nan"), "test": float("nan")}
         obj = [(r[m], t[m]) for r, t, m in zip(rgbs, targets, masks) if m.any()]
         psnr_obj = self.psnr([a for a, _ in obj], [b for _, b in obj], name="PSNR_obj") if obj else {"name": "PSNR_obj", "mean": float("nan"), "test": float("nan")}
         self.log("test/psnr", psnr["test"])
+        self.log("test/ssim", ssim["test"])
         self.log("test/psnr_obj", psnr_obj["test"])
         if self.trainer.is_global_zero:
             exp, ren = getattr(self.hparams, "exp_name", "exp"), getattr(self.hparams, "render_name", "render")
             image_dir = os.path.join(getattr(self.hparams, "ckpt_root", "ckpts"), exp, ren)
             os.makedirs(image_dir, exist_ok=True)
             store_image(image_dir, rgbs, "image")
-            write_stats(os.path.join(os.path.dirname(image_dir), "results.json"), psnr, psnr_obj)
-        return psnr, psnr_obj
+            write_stats(os.path.join(os.path.dirname(image_dir), "results.json"), psnr, ssim, psnr_obj)
+        return psnr, ssim, psnr_obj
 
     @staticmethod
     def _squeeze(batch, keep=()):

@@ -54,7 +54,7 @@ def test_run_cli_train_then_eval(tmp_path, built_lib, monkeypatch):
     s = run.main(run.get_opts(common + ["--run_eval", "--render_name", "rr", "--precision", "f16x3"]))
     assert sorted(os.listdir(tmp_path / "ckpts" / "t" / "rr")) == ["image000.jpg", "image001.jpg"]
     res = json.load(open(tmp_path / "ckpts" / "t" / "results.json"))
-    assert set(res) == {"PSNR", "PSNR_obj"} and set(res["PSNR"]) == {"mean", "test"}
+    assert set(res) == {"PSNR", "SSIM", "PSNR_obj"} and set(res["PSNR"]) == {"mean", "test"}
     assert abs(res["PSNR"]["test"] - s.logged["test/psnr"]) < 1e-6
 
 

@@ -60,3 +60,33 @@ def test_flat_adam_refuses_cpu_parameters(built_lib):
     s = lit.LitNeRF(_hp())
     with pytest.raises(lib.AonError):
         s.configure_optimizers()
+
+
+def test_ssim_matches_an_independent_evaluation(built_lib):
+    """lit ssim_each (interface.py:102-112 computes piqa.SSIM(); piqa is absent, the metric is restated from its definition)
+    against an independent float64 numpy / scipy evaluation of the same definition: 11-tap Gaussian (sigma 1.5), valid
+    windows, k1 = 0.01, k2 = 0.03, mean over channels and pixels; identical images give exactly 1."""
+    import numpy as np
+    import torch
+    from scipy.ndimage import correlate1d
+    from aon_b200 import lit
+    g = torch.Generator().manual_seed(0)
+    H, W = 37, 52
+    gt = torch.rand(H, W, 3, generator=g)
+    pred = (gt + 0.1 * torch.randn(H, W, 3, generator=g)).clamp(-0.2, 1.2)       # exercises the clip to [0, 1]
+    m = lit._LitCommon()
+    got = m.ssim_each([pred, gt], [gt, gt])
+    assert abs(got[1].item() - 1.0) < 1e-6
+
+    k = np.exp(-(np.arange(11) - 5.0) ** 2 / (2 * 1.5 ** 2)); k /= k.sum()
+    blur = lambda a: correlate1d(correlate1d(a, k, axis=0, mode="constant"), k, axis=1, mode="constant")[5:-5, 5:-5]
+    x, y = np.clip(pred.double().numpy(), 0, 1), np.clip(gt.double().numpy(), 0, 1)
+    vals = []
+    for c in range(3):
+        mx, my = blur(x[..., c]), blur(y[..., c])
+        sxx, syy, sxy = blur(x[..., c] ** 2) - mx ** 2, blur(y[..., c] ** 2) - my ** 2, blur(x[..., c] * y[..., c]) - mx * my
+        cs = (2 * sxy + 0.03 ** 2) / (sxx + syy + 0.03 ** 2)
+        vals.append(((2 * mx * my + 0.01 ** 2) / (mx ** 2 + my ** 2 + 0.01 ** 2) * cs))
+    want = float(np.mean(np.stack(vals)))
+    assert abs(got[0].item() - want) < 1e-5, (got[0].item(), want)
+    assert 0.0 < want < 0.999
